@@ -1,0 +1,72 @@
+// Internal declarations shared by the CUDA translation units of libiaf_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/iaf_b200.h"
+
+#define IAF_NTAPS 5          // live taps of the 3x3 AR mask: (ky,kx) = (1,1)c (1,2) (2,0) (2,1) (2,2)
+#define IAF_MAX_STAGES (IAF_MAX_HIDDEN + 1)
+
+// One conv stage as the SIMT kernel sees it (weights already masked, normalised, scaled).
+struct IafStageDev {
+  const float* w;     // [5][cin][cout_pad], cout contiguous (heads: see iaf_pack.cu for the column order)
+  const float* bias;  // [cout_pad]
+  const float* padw;  // [4][cout_pad]: Theano pad-channel weights of taps 1..4, nullptr for TF
+  int cin, cout, cout_pad;
+};
+
+struct IafSimtParams {
+  // inputs
+  const float* z;          // [B,C,H,W]   (layer mode: eps)
+  const float* ctx;        // [B,hidden0,H,W]
+  const float* post_mean;  // layer mode only
+  const float* post_logsd;
+  const float* prior_mean;
+  const float* prior_logsd;
+  // outputs (nullable)
+  float* z_out;
+  float* logsd_out;        // step mode: arw_logsd; layer mode: kl per element
+  float* m_out;            // multiconv mode: head 0
+  float* s_out;            // multiconv mode: head 1
+  float* bc_out;           // layer mode: [B,C] sum over (h,w) of kl
+  float* persample_out;    // step: logdet [B]; layer: kl_cost [B]
+  float* partial;          // [B][n_bands][C] per-band per-channel partial sums
+  unsigned* counter;       // [B] band arrival counters (self-resetting)
+  IafStageDev stage[IAF_MAX_STAGES];
+  int n_stages;            // n_hidden + 1 (last = heads)
+  int n_heads, head_c, head_pad;
+  int B, C, H, W, P;       // P = smem row pitch = 8*ceil(W/8) + 2
+  int band_rows, n_bands;
+  int flip;                // 1: Theano orientation (data point-reflected on load/store)
+  int nl;
+  int mode;                // 0 multiconv, 1 step, 2 layer
+  float scale;             // 0.1
+  int bufz_elems, bufa_elems, bufb_elems;
+};
+
+enum { IAF_MODE_MULTICONV = 0, IAF_MODE_STEP = 1, IAF_MODE_LAYER = 2 };
+
+// Raw-parameter description handed to the pack kernel.
+struct IafPackLayer {
+  const float* w;      // reference layout (TF [3,3,Cin,Cout] | Theano [Cout,Cin+1,3,3])
+  const float* scale;  // g | s
+  const float* bias;   // b
+  float* w_out;        // simt packed
+  float* bias_out;
+  float* padw_out;     // Theano only
+  int cin, cout, cout_pad;
+  int zerodiag;        // heads: 1
+  int head_pairs;      // 1: two equal heads interleaved in groups of 4 columns (m0..3,s0..3,...)
+  int head_c, head_pad;
+  int col0;            // first packed column this (head) layer owns when head_pairs (0 or 4)
+};
+
+struct IafPackParams {
+  IafPackLayer layer[IAF_MAX_HIDDEN + IAF_MAX_HEADS];
+  int n_layers;
+  int variant;
+};
+
+cudaError_t iaf_launch_pack(const IafPackParams& p, int max_cout, cudaStream_t stream);
+cudaError_t iaf_launch_simt(const IafSimtParams& p, size_t smem_bytes, cudaStream_t stream);
+cudaError_t iaf_simt_set_smem(size_t smem_bytes);

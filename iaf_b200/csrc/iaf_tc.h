@@ -1,0 +1,27 @@
+// Tensor-core (tcgen05) path of the IAF step: internal interface used by iaf_capi.cu.
+#pragma once
+#include "iaf_common.h"
+
+struct IafTcPlan;
+
+struct IafTcArgs {
+  int mode;  // IAF_MODE_STEP | IAF_MODE_LAYER
+  const float* z;  // layer mode: eps
+  const float* ctx;
+  const float* post_mean;
+  const float* post_logsd;
+  const float* prior_mean;
+  const float* prior_logsd;
+  float* z_out;
+  float* elem_out;       // arw_logsd | kl, nullable
+  float* bc_out;         // [B,C], nullable
+  float* persample_out;  // [B], nullable
+  int B;
+};
+
+bool iaf_tc_supported(const iaf_desc_t* d);
+int iaf_tc_plan_create(IafTcPlan** out, const iaf_desc_t* d);
+void iaf_tc_plan_destroy(IafTcPlan* p);
+int iaf_tc_pack(IafTcPlan* p, const float* const* w, const float* const* scale, const float* const* bias,
+                cudaStream_t stream);
+int iaf_tc_run(IafTcPlan* p, const IafTcArgs* a, cudaStream_t stream, int* n_launches);

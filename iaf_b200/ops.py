@@ -1,0 +1,315 @@
+"""Host side of the B200 IAF step: the reference's python operator signatures over the C ABI.
+
+PyTorch tensors are used as device storage and for the current stream only; all compute
+is in libiaf_b200.so (include/iaf_b200.h).  Three entry points mirror the reference:
+
+* ``ar_multiconv2d(name, x, context, n_h, n_out, nl, params=...)``
+      tf_utils/layers.py:158-166 (called at tf_train.py:69)
+* ``multiconv2d(name, n_in, n_h, n_out, size_kernel, flipmask, nl, w)`` -> callable
+      graphy/nodes/ar.py:378-423 (called at models.py:92,170,281)
+* ``iaf_step(z, context, ...)`` -- the fused superset: the stack plus the caller's
+      ``arw_mean*=.1; arw_logsd*=.1; z=(z-arw_mean)/exp(arw_logsd); logqs+=arw_logsd``
+      (models.py:282-285, tf_train.py:70-72)
+
+Both reference functions are graph builders called once; here they run eagerly per batch,
+so the masked / normalised / packed weights are cached on the operator and re-packed only
+when a parameter tensor changes.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .masks import theano_conv_ar_mask
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _check_input(t, name, shape=None):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise RuntimeError("iaf_b200: %s is on %s; this operator only runs on CUDA (no CPU fallback)" % (name, t.device))
+    if t.dtype != torch.float32:
+        raise TypeError("%s must be float32 (reference floatX / tf.float32), got %s" % (name, t.dtype))
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise ValueError("%s has shape %s, expected %s" % (name, tuple(t.shape), tuple(shape)))
+    return t.contiguous()
+
+
+class IAFOperator(object):
+    """One masked-AR conv stack (+ fused affine update) bound to raw reference parameters.
+
+    variant: "tf" (tf_utils/layers.py numerics) or "theano" (graphy/nodes/ar.py numerics).
+    layers:  list of (w, scale, bias) tensors, hidden layers first then heads, in the
+             reference's layouts: tf V [3,3,Cin,Cout], g, b; theano w [Cout,Cin+1,3,3], s, b.
+    """
+
+    def __init__(self, variant, n_z, hidden, heads, nl="elu", path="auto"):
+        if variant not in _lib.VARIANTS:
+            raise ValueError("variant must be 'tf' or 'theano'")
+        if nl not in _lib.NLS:
+            raise NotImplementedError("nonlinearity %r is not available in the fused kernel" % (nl,))
+        if path not in _lib.PATHS:
+            raise ValueError("path must be one of %s" % sorted(_lib.PATHS))
+        hidden, heads = [int(h) for h in hidden], [int(h) for h in heads]
+        if len(hidden) > _lib.IAF_MAX_HIDDEN:
+            raise NotImplementedError("at most %d hidden layers" % _lib.IAF_MAX_HIDDEN)
+        if not 1 <= len(heads) <= _lib.IAF_MAX_HEADS:
+            raise NotImplementedError("n_out must have 1 or 2 entries")
+        self.variant, self.n_z, self.hidden, self.heads, self.nl, self.path = variant, int(n_z), hidden, heads, nl, path
+        self._layers = None
+        self._plans = {}      # (H, W, device index) -> [handle, packed_key]
+        self._lib = _lib.lib()
+
+    # ---- parameters ---------------------------------------------------------------
+    def set_weights(self, layers):
+        n = len(self.hidden) + len(self.heads)
+        if len(layers) != n:
+            raise ValueError("expected %d (w, scale, bias) triples, got %d" % (n, len(layers)))
+        sizes = [self.n_z] + self.hidden
+        out = []
+        for i, (w, s, b) in enumerate(layers):
+            cin = sizes[min(i, len(self.hidden))]
+            cout = self.hidden[i] if i < len(self.hidden) else self.heads[i - len(self.hidden)]
+            wshape = (3, 3, cin, cout) if self.variant == "tf" else (cout, cin + 1, 3, 3)
+            out.append((_check_input(w, "w[%d]" % i, wshape), _check_input(s, "scale[%d]" % i, (cout,)),
+                        _check_input(b, "bias[%d]" % i, (cout,))))
+        self._layers = out
+        return self
+
+    def _weights_key(self):
+        return tuple((t.data_ptr(), t._version) for l in self._layers for t in l)
+
+    # ---- plans ----------------------------------------------------------------------
+    def _plan(self, H, W, device):
+        key = (H, W, device.index)
+        ent = self._plans.get(key)
+        if ent is None:
+            d = _lib.IafDesc()
+            d.variant = _lib.VARIANTS[self.variant]
+            d.n_z = self.n_z
+            d.n_hidden = len(self.hidden)
+            for i, h in enumerate(self.hidden):
+                d.hidden[i] = h
+            d.n_heads = len(self.heads)
+            for i, h in enumerate(self.heads):
+                d.head[i] = h
+            d.H, d.W = H, W
+            d.nl = _lib.NLS[self.nl]
+            d.path = _lib.PATHS[self.path]
+            handle = C.c_void_p()
+            with torch.cuda.device(device):
+                _lib.check(self._lib.iaf_plan_create(C.byref(handle), C.byref(d)))
+            ent = [handle, None]
+            self._plans[key] = ent
+        if self._layers is None:
+            raise RuntimeError("IAFOperator.set_weights() has not been called")
+        wk = self._weights_key()
+        if ent[1] != wk:
+            n = len(self._layers)
+            arr = lambda j: (C.c_void_p * n)(*[l[j].data_ptr() for l in self._layers])
+            with torch.cuda.device(device):
+                _lib.check(self._lib.iaf_pack_weights(ent[0], arr(0), arr(1), arr(2), _stream(device)))
+            ent[1] = wk
+        return ent[0]
+
+    def __del__(self):
+        try:
+            for ent in self._plans.values():
+                self._lib.iaf_plan_destroy(ent[0])
+        except Exception:
+            pass
+
+    # ---- introspection --------------------------------------------------------------
+    def path_used(self, H, W, device):
+        return _lib.PATH_NAMES[self._lib.iaf_plan_path(self._plan(H, W, torch.device(device)))]
+
+    def launch_count(self):
+        return sum(int(self._lib.iaf_plan_launch_count(e[0])) for e in self._plans.values())
+
+    def algorithmic_bytes(self, B, H, W, device):
+        return int(self._lib.iaf_plan_algorithmic_bytes(self._plan(H, W, torch.device(device)), B))
+
+    def algorithmic_flops(self, B, H, W, device):
+        return float(self._lib.iaf_plan_algorithmic_flops(self._plan(H, W, torch.device(device)), B))
+
+    # ---- calls ----------------------------------------------------------------------
+    def _shapes(self, z, context):
+        z = _check_input(z, "z")
+        if z.dim() != 4 or z.shape[1] != self.n_z:
+            raise ValueError("z must be [B,%d,H,W], got %s" % (self.n_z, tuple(z.shape)))
+        B, _, H, W = z.shape
+        if self.hidden:
+            context = _check_input(context, "context", (B, self.hidden[0], H, W))
+            if context.device != z.device:
+                raise ValueError("z and context are on different devices")
+        else:
+            context = None  # never added when there is no hidden layer (ar.py:399-403)
+        return z, context, B, H, W
+
+    def multiconv(self, z, context):
+        """The un-fused stack: list of head outputs (ar.py:396-416 / layers.py:158-166)."""
+        z, context, B, H, W = self._shapes(z, context)
+        plan = self._plan(H, W, z.device)
+        outs = [torch.empty((B, h, H, W), device=z.device, dtype=torch.float32) for h in self.heads]
+        arr = (C.c_void_p * len(outs))(*[o.data_ptr() for o in outs])
+        with torch.cuda.device(z.device):
+            _lib.check(self._lib.iaf_multiconv_fwd(plan, _ptr(z), _ptr(context), arr, B, _stream(z.device)))
+        return outs
+
+    def step(self, z, context, want_logsd=True, want_logdet=True):
+        """(z', arw_logsd [B,C,H,W], logdet [B]); logqs_new = logqs + arw_logsd."""
+        z, context, B, H, W = self._shapes(z, context)
+        plan = self._plan(H, W, z.device)
+        z_out = torch.empty_like(z)
+        logsd = torch.empty_like(z) if want_logsd else None
+        logdet = torch.empty((B,), device=z.device, dtype=torch.float32) if want_logdet else None
+        with torch.cuda.device(z.device):
+            _lib.check(self._lib.iaf_step_fwd(plan, _ptr(z), _ptr(context), _ptr(z_out), _ptr(logsd), _ptr(logdet),
+                                              B, _stream(z.device)))
+        return z_out, logsd, logdet
+
+    def step_host(self, z, context, z_out, logsd_out, logdet_out):
+        """End-to-end entry on HOST tensors (pinned or pageable): H2D, step, D2H, sync."""
+        for t in (z, context, z_out, logsd_out, logdet_out):
+            if t is not None and (t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous()):
+                raise ValueError("step_host takes contiguous float32 CPU tensors")
+        B, _, H, W = z.shape
+        device = torch.device("cuda", torch.cuda.current_device())
+        plan = self._plan(H, W, device)
+        _lib.check(self._lib.iaf_step_fwd_host(plan, _ptr(z), _ptr(context), _ptr(z_out), _ptr(logsd_out),
+                                               _ptr(logdet_out), B, _stream(device)))
+        return z_out, logsd_out, logdet_out
+
+    def layer(self, eps, post_mean, post_logsd, prior_mean, prior_logsd, context, want_kl=True):
+        """Fused posterior-sample -> IAF step -> KL block (tf_train.py:56-85, models.py:273-328).
+        Returns (z', kl [B,C,H,W] or None, kl_bc [B,C], kl_cost [B])."""
+        eps, context, B, H, W = self._shapes(eps, context)
+        ts = [_check_input(t, n, eps.shape) for t, n in ((post_mean, "post_mean"), (post_logsd, "post_logsd"),
+                                                          (prior_mean, "prior_mean"), (prior_logsd, "prior_logsd"))]
+        plan = self._plan(H, W, eps.device)
+        z_out = torch.empty_like(eps)
+        kl = torch.empty_like(eps) if want_kl else None
+        kl_bc = torch.empty((B, self.n_z), device=eps.device, dtype=torch.float32)
+        kl_cost = torch.empty((B,), device=eps.device, dtype=torch.float32)
+        with torch.cuda.device(eps.device):
+            _lib.check(self._lib.iaf_layer_fwd(plan, _ptr(eps), _ptr(ts[0]), _ptr(ts[1]), _ptr(ts[2]), _ptr(ts[3]),
+                                               _ptr(context), _ptr(z_out), _ptr(kl), _ptr(kl_bc), _ptr(kl_cost), B,
+                                               _stream(eps.device)))
+        return z_out, kl, kl_bc, kl_cost
+
+
+# ------------------------------------------------------------------------------------
+# TF-style entry: tf_utils/layers.py:158-166
+# ------------------------------------------------------------------------------------
+_TF_OPS = {}
+
+
+def _tf_layers(name, params, n_h, n_out):
+    """Collect V/g/b under the TF variable names ``{name}/layer_{i}/{V,g,b}`` and
+    ``{name}/layer_out_{k}/...`` (layers.py:160-166, 53-55); the ``{name}/`` prefix is optional."""
+    def get(scope, k):
+        for key in ("%s/%s/%s" % (name, scope, k), "%s/%s" % (scope, k)):
+            if key in params:
+                return params[key]
+        raise KeyError("parameter %s/%s/%s not found" % (name, scope, k))
+    layers = [tuple(get("layer_%d" % i, k) for k in "Vgb") for i in range(len(n_h))]
+    layers += [tuple(get("layer_out_%d" % i, k) for k in "Vgb") for i in range(len(n_out))]
+    return layers
+
+
+def _nl_name(nl):
+    if callable(nl):
+        nl = getattr(nl, "__name__", str(nl))
+    return nl
+
+
+def ar_multiconv2d(name, x, context, n_h, n_out, nl="elu", params=None, path="auto", **_):
+    """Drop-in for tf_utils/layers.py:ar_multiconv2d -> list of tensors (one per n_out entry).
+    ``params`` stands in for the TF variable scope: a dict holding V/g/b under the TF names."""
+    if params is None:
+        raise ValueError("params (the variable store) is required in eager mode")
+    nl = _nl_name(nl)
+    key = (name, id(params), tuple(n_h), tuple(n_out), nl, path)
+    op = _TF_OPS.get(key)
+    if op is None:
+        op = IAFOperator("tf", x.shape[1], n_h, n_out, nl=nl, path=path)
+        _TF_OPS[key] = op
+    op.set_weights(_tf_layers(name, params, n_h, n_out))
+    return op.multiconv(x, context)
+
+
+# ------------------------------------------------------------------------------------
+# Theano-style factory: graphy/nodes/ar.py:378-423
+# ------------------------------------------------------------------------------------
+class _Struct(object):  # graphy/__init__.py:35-39
+    def __init__(self, **entries):
+        self.__dict__.update(entries)
+
+    def __call__(self, *a, **k):
+        return self.__dict__["__call__"](*a, **k)
+
+
+def multiconv2d(name, n_in, n_h, n_out, size_kernel=(3, 3), flipmask=False, nl="relu", w=None, device="cuda",
+                path="auto"):
+    """Drop-in for graphy/nodes/ar.py:multiconv2d.  Creates the parameters the reference creates
+    (``{name}_{i}_w/_b/_s`` and ``{name}_out_{k}_w/_b/_s``, ar.py:288-296) in ``w`` if absent and
+    returns an object with ``__call__(h, context, w, return_hiddens=False)``, ``w`` and ``postup``."""
+    if w is None:
+        w = {}
+    if not isinstance(n_out, list) and isinstance(n_out, int):
+        n_out = [n_out]
+    if tuple(size_kernel) != (3, 3):
+        raise NotImplementedError("only the 3x3 kernel the reference uses (train.py:63) is implemented")
+    if flipmask:
+        raise NotImplementedError("flipmask=True is never used on the down_iaf2_nl / up_iaf2_nl path (models.py:92)")
+    sizes = [n_in] + list(n_h)
+    names, masks = [], []
+    specs = [(name + "_" + str(i), sizes[i], sizes[i + 1], False) for i in range(len(n_h))]
+    specs += [(name + "_out_" + str(i), sizes[-1], n_out[i], True) for i in range(len(n_out))]
+    for lname, cin, cout, zd in specs:
+        assert cin % cout == 0 or cout % cin == 0  # ar.py:250,257
+        mask = theano_conv_ar_mask(cin, cout, (3, 3), zd)
+        if lname + "_w" not in w:  # ar.py:288, 293-296
+            w[lname + "_w"] = torch.from_numpy(mask * 0.05 * np.random.randn(cout, cin + 1, 3, 3)).float().to(device)
+            w[lname + "_b"] = torch.zeros(cout, device=device)
+            w[lname + "_s"] = torch.zeros(cout, device=device)
+        names.append(lname)
+        masks.append(mask)
+    op = IAFOperator("theano", n_in, n_h, n_out, nl=nl, path=path)
+
+    def f(h, context, w, return_hiddens=False):
+        if return_hiddens:
+            raise NotImplementedError("return_hiddens=True: hidden activations never leave the SM in the fused kernel")
+        op.set_weights([(w[n + "_w"], w[n + "_s"], w[n + "_b"]) for n in names])
+        out = op.multiconv(h, context)
+        if len(n_out) == 1:
+            out = out[0]  # ar.py:411
+        return out
+
+    def postup(updates, w):
+        """ar.py:369-373: re-apply the mask to an updated weight.  ``updates`` maps parameter
+        name -> new value (Theano keys by shared variable; names are the eager equivalent)."""
+        for n, m in zip(names, masks):
+            if n + "_w" in updates:
+                u = updates[n + "_w"]
+                updates[n + "_w"] = u * torch.from_numpy(m).to(u.device, u.dtype)
+        return updates
+
+    return _Struct(__call__=f, w=w, postup=postup, op=op, names=names)
+
+
+# ------------------------------------------------------------------------------------
+# fused entry
+# ------------------------------------------------------------------------------------
+def iaf_step(z, context, op):
+    """(z', arw_logsd_elem, logdet_per_sample) for an IAFOperator with weights set."""
+    return op.step(z, context)

@@ -1,0 +1,148 @@
+/*
+ * iaf_b200 -- C ABI of the B200-native IAF posterior step.
+ *
+ * The reference (openai/iaf) has no FFI layer: its boundary for this path is a python
+ * callable.  These entry points are what a python (ctypes/cffi) binding of that callable
+ * binds; each comment names the reference interface the function replaces
+ * (paths relative to the reference repo).  Plain pointers and sizes only -- no torch,
+ * no CUDA types in the signatures (streams travel as void*; NULL = default stream).
+ *
+ * All tensors are fp32, NCHW, contiguous.  Device pointers unless a name ends in _host.
+ * Every function returns IAF_OK (0) or a negative iaf_status; nothing here ever falls
+ * back to a CPU path.
+ */
+#ifndef IAF_B200_H
+#define IAF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IAF_MAX_HIDDEN 4
+#define IAF_MAX_HEADS 2
+
+typedef enum {
+  IAF_OK = 0,
+  IAF_ERR_BAD_ARG = -1,     /* NULL pointer, non-positive size                               */
+  IAF_ERR_BAD_SHAPE = -2,   /* the asserts of ar.py:225-257 / layers.py:116 (divisibility)    */
+  IAF_ERR_UNSUPPORTED = -3, /* valid in the reference but outside what the kernels cover       */
+  IAF_ERR_CUDA = -4,        /* a CUDA runtime call failed; see iaf_last_cuda_error()           */
+  IAF_ERR_NOT_PACKED = -5,  /* iaf_step_* called before iaf_pack_weights                       */
+  IAF_ERR_NO_DEVICE = -6    /* no sm_100 device                                                */
+} iaf_status;
+
+/* which of the reference's two implementations the numerics follow */
+typedef enum {
+  IAF_VARIANT_TF = 0,    /* tf_utils/layers.py: SAME zero pad, cross-correlation, exp(g)*rsqrt(max(ss,1e-12)) */
+  IAF_VARIANT_THEANO = 1 /* graphy/nodes/ar.py: pad channel, true convolution, exp(3s)/(sqrt(ss)+1e-8)        */
+} iaf_variant;
+
+/* graphy/nodes/__init__.py:158-177 (parameter-free entries); tf.nn.elu */
+typedef enum { IAF_NL_NONE = 0, IAF_NL_ELU = 1, IAF_NL_SOFTPLUS = 2, IAF_NL_RELU = 3, IAF_NL_TANH = 4, IAF_NL_LEAKYRELU = 5 } iaf_nl;
+
+typedef enum {
+  IAF_PATH_AUTO = 0, /* tensor cores when the shape qualifies, else SIMT            */
+  IAF_PATH_SIMT = 1, /* exact-fp32 FMA kernel (parity anchor, any shape)            */
+  IAF_PATH_TC = 2    /* tcgen05 implicit-GEMM kernel, bf16x3 split operands         */
+} iaf_path;
+
+/*
+ * Static description of one masked-AR conv stack; the arguments of
+ *   multiconv2d(name, n_in, n_h, n_out, size_kernel, flipmask, nl, w)   graphy/nodes/ar.py:378
+ *   ar_multiconv2d(name, x, context, n_h, n_out, nl)                     tf_utils/layers.py:159
+ * size_kernel is fixed to 3x3 (the only size either caller uses: train.py:63, layers.py:145)
+ * and flipmask to False (models.py:92).
+ */
+typedef struct iaf_desc {
+  int variant;                /* iaf_variant                                               */
+  int n_z;                    /* n_in: channels of z                                        */
+  int n_hidden;               /* len(n_h): 0..IAF_MAX_HIDDEN (0 only meaningful for Theano, F8) */
+  int hidden[IAF_MAX_HIDDEN]; /* n_h                                                        */
+  int n_heads;                /* len(n_out): 1 or 2                                         */
+  int head[IAF_MAX_HEADS];    /* n_out; two heads must have equal size                     */
+  int H, W;                   /* feature-map size                                           */
+  int nl;                     /* iaf_nl                                                     */
+  int path;                   /* iaf_path                                                   */
+} iaf_desc_t;
+
+typedef struct iaf_plan iaf_plan_t; /* opaque: packed weights, scratch, launch geometry */
+
+/* Validate the description and allocate the plan (replaces the graph-construction half of
+ * ar.multiconv2d, ar.py:378-394, incl. its asserts).  */
+int iaf_plan_create(iaf_plan_t** plan, const iaf_desc_t* desc);
+void iaf_plan_destroy(iaf_plan_t* plan);
+
+/*
+ * Weight preparation, one fused kernel (replaces the per-call graph ops of
+ * layers.py:53-60 and ar.py:312-321 + 267-281 + the mask constants of layers.py:134-141 /
+ * ar.py:241-264).  Arrays have n_hidden + n_heads entries, hidden layers first, in the
+ * reference's own layouts and names:
+ *   TF:     w[i] = V [3,3,Cin,Cout], scale[i] = g [Cout], bias[i] = b [Cout]
+ *   Theano: w[i] = {name}_w [Cout,Cin+1,3,3], scale[i] = {name}_s [Cout], bias[i] = {name}_b [Cout]
+ * Raw (un-masked, un-normalised) parameters go in; masking is applied here, which also
+ * makes the postup() re-masking of ar.py:369-373 unnecessary for the forward pass.
+ */
+int iaf_pack_weights(iaf_plan_t* plan, const float* const* w, const float* const* scale,
+                     const float* const* bias, void* stream);
+
+/*
+ * The un-fused operator: outs[k] = head k of the masked-AR stack, i.e. exactly what
+ *   posterior_conv1(z, context, w)            models.py:170,281 (ar.py:396-416)
+ *   ar_multiconv2d(name, z, context, ...)     tf_train.py:69    (layers.py:158-166)
+ * return (before the caller's *0.1).  z [B,n_z,H,W], context [B,hidden[0],H,W]
+ * (ignored when n_hidden == 0), outs[k] [B,head[k],H,W].
+ */
+int iaf_multiconv_fwd(iaf_plan_t* plan, const float* z, const float* context, float* const* outs,
+                      int B, void* stream);
+
+/*
+ * The fused IAF step (the hot path): stack + the caller's three lines
+ *   arw_mean*=.1; arw_logsd*=.1; z=(z-arw_mean)/exp(arw_logsd); logqs+=arw_logsd
+ *   models.py:282-285, models.py:171-175, tf_train.py:70-72
+ * z_out [B,n_z,H,W]; logsd_out [B,n_z,H,W] = arw_logsd (the per-element term the ELBO
+ * consumes, F7; may be NULL); logdet_out [B] = -sum_{c,h,w} arw_logsd (may be NULL).
+ * Needs n_heads == 2 and head[0] == head[1] == n_z.
+ */
+int iaf_step_fwd(iaf_plan_t* plan, const float* z, const float* context, float* z_out,
+                 float* logsd_out, float* logdet_out, int B, void* stream);
+
+/*
+ * Same step, host buffers: copies z/context H2D, runs iaf_step_fwd, copies the results
+ * D2H and synchronises.  Buffers may be pageable or pinned (pinned for speed); device
+ * staging belongs to the plan and grows on demand.  This is the end-to-end entry
+ * bench.py's "e2e" times.
+ */
+int iaf_step_fwd_host(iaf_plan_t* plan, const float* z_host, const float* context_host,
+                      float* z_out_host, float* logsd_out_host, float* logdet_out_host, int B,
+                      void* stream);
+
+/*
+ * The stochastic-layer block around the step, fused:
+ *   tf_train.py:56-85 / models.py:273-298: posterior sample from the given noise, logqs,
+ *   the IAF step, prior logps at z', kl = logqs - logps and its reductions.
+ * post_mean/post_logsd: the posterior's mean and log-sd (rz+qz, already summed by the
+ * caller: one add each, tf_train.py:57); eps: N(0,1) noise; prior_mean/prior_logsd.
+ * Outputs: z_out [B,n_z,H,W]; kl_out [B,n_z,H,W] (may be NULL); kl_bc_out [B,n_z]
+ * = sum_{h,w} kl (what the free-bits term consumes, may be NULL); kl_cost_out [B]
+ * = sum_{c,h,w} kl (may be NULL).
+ */
+int iaf_layer_fwd(iaf_plan_t* plan, const float* eps, const float* post_mean, const float* post_logsd,
+                  const float* prior_mean, const float* prior_logsd, const float* context,
+                  float* z_out, float* kl_out, float* kl_bc_out, float* kl_cost_out, int B, void* stream);
+
+/* introspection */
+const char* iaf_strerror(int status);
+const char* iaf_last_cuda_error(void);          /* message of the last failing CUDA call (thread-local) */
+int iaf_version(void);                          /* 10000*major + 100*minor + patch                      */
+int iaf_plan_path(const iaf_plan_t* plan);      /* iaf_path actually selected (SIMT or TC)              */
+uint64_t iaf_plan_launch_count(const iaf_plan_t* plan); /* kernels launched through this plan so far    */
+size_t iaf_plan_algorithmic_bytes(const iaf_plan_t* plan, int B); /* SURVEY 8d bytes of one iaf_step_fwd */
+double iaf_plan_algorithmic_flops(const iaf_plan_t* plan, int B); /* 2*B*H*W*sum nnz(mask)              */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IAF_B200_H */
