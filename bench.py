@@ -158,6 +158,23 @@ def cpu_port_runner(name, layers_cpu, sample_B, threads):
     return fn, sample_B * n_z * H * W
 
 
+def best_thread_count(fn, max_threads):
+    """The reference's framework would pick its own thread count; more threads than the convs can
+    use makes torch slower, so probe a few settings and keep the fastest."""
+    best, best_t = max_threads, None
+    cands = sorted({c for c in (8, 16, 32, 64, max_threads) if c <= max_threads})
+    for c in cands:
+        torch.set_num_threads(c)
+        fn()
+        t0 = time.perf_counter()
+        fn()
+        dt = time.perf_counter() - t0
+        if best_t is None or dt < best_t:
+            best, best_t = c, dt
+    torch.set_num_threads(best)
+    return best
+
+
 def time_cpu(fn, warmup, steps):
     for _ in range(warmup):
         fn()
@@ -185,6 +202,7 @@ def run_reference(args, rank, world):
     # bounded sample: the full 256-sample batch per step, at most 50 steps
     sample_B = B
     fn, elems = cpu_port_runner(name, layers, sample_B, threads)
+    threads = best_thread_count(fn, threads)
     steps = max(1, min(args.steps, 50))
     warm = max(1, min(args.warmup, 3))
     t = time_cpu(fn, warm, steps)
@@ -383,6 +401,7 @@ def main():
         threads = os.cpu_count() or 1
         sample_B = B
         fn, elems = cpu_port_runner(name, layers_cpu, sample_B, threads)
+        threads = best_thread_count(fn, threads)
         t1 = time_cpu(fn, 2, 1)
         reps = int(max(3, min(200, 15.0 / max(t1, 1e-4))))
         t = time_cpu(fn, 0, reps)

@@ -277,8 +277,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
       const IafTcStage& St = p.st[j];
       const uint32_t d_tmem = tmem_base + (uint32_t)St.tmem_col;
 
-      // ---- MMA issue (one thread) ----
-      if (tid == 0) {
+      // ---- MMA issue: one thread; the rest of its warp parks at __syncwarp so that no lane of the
+      //      issuing warp sits in mbarrier.try_wait (which suspends the whole warp) meanwhile ----
+      if (warp == 0) {
+       if (lane == 0) {
         if (!weights_ready) mbar_wait(&bar_w, 0);
         tc_fence_after();
         const uint32_t idesc = umma_idesc(St.N);
@@ -301,6 +303,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
           }
         }
         umma_commit(&bar_mma);
+       }
+       __syncwarp();
       }
       weights_ready = true;
       mbar_wait(&bar_mma, mma_parity);
