@@ -57,6 +57,7 @@ struct iaf_plan {
   size_t w_elems[IAF_MAX_STAGES];
   int head_pad;
   bool packed;
+  bool simt_ok;
   // SIMT geometry
   int band_rows, n_bands, P;
   int bufz, bufa, bufb, tilepart;
@@ -201,6 +202,7 @@ int iaf_plan_create(iaf_plan_t** out, const iaf_desc_t* desc) {
   }
   bool simt_ok = chosen > 0;
   if (simt_ok) simt_geometry(pl, chosen, nullptr);
+  pl->simt_ok = simt_ok;
 
   // tensor-core path
   pl->tc = nullptr;
@@ -295,7 +297,7 @@ static int run(iaf_plan* pl, int mode, const float* z, const float* ctx, const f
   if (!pl->packed) return IAF_ERR_NOT_PACKED;
   if (B <= 0) return IAF_ERR_BAD_ARG;
   const iaf_desc_t& d = pl->d;
-  if (pl->path == IAF_PATH_TC && mode != IAF_MODE_MULTICONV) {
+  if (pl->path == IAF_PATH_TC && mode != IAF_MODE_MULTICONV && iaf_tc_mode_supported(pl->tc, mode)) {
     IafTcArgs a;
     memset(&a, 0, sizeof(a));
     a.mode = mode; a.z = z; a.ctx = ctx; a.post_mean = post_mean; a.post_logsd = post_logsd;
@@ -307,6 +309,7 @@ static int run(iaf_plan* pl, int mode, const float* z, const float* ctx, const f
     pl->launches += nl;
     return st;
   }
+  if (!pl->simt_ok) return IAF_ERR_UNSUPPORTED;
   int st = ensure_scratch(pl, B);
   if (st != IAF_OK) return st;
   IafSimtParams p;

@@ -20,11 +20,15 @@
 // hi*hi + lo*hi + hi*lo, fp32 accumulation in TMEM.  Roofline numbers are always quoted
 // on ALGORITHMIC flops, not on the 3x issued.
 //
-// Dependencies only run forward in the stream (a slot needs slots s .. s+Wp+1 of the layer
-// below), so a CTA walks a contiguous run of tiles as a wavefront: layer j works on tile
-// t-j, intermediate layers keep a 2-tile ring (+ a mirrored margin so a shifted 128-row
-// window never wraps).  Orientation of the Theano variant: see iaf_simt.cu (point
-// reflection on load/store).
+// Schedule.  Dependencies only run forward in the stream (a slot needs slots s .. s+Wp+1 of
+// the layer below), so a CTA walks a contiguous run of tiles as a wavefront.  One control
+// warp issues every tcgen05.mma; 16 worker warps (4 per TMEM lane quadrant, splitting the
+// accumulator columns) load z, run the epilogues and write the next layer's operand ring.
+// In period s the tensor pipe runs M_j(s+1-2j) while the workers run L(s+1), E_j(s-2j):
+// accumulators are double-buffered in TMEM, operand rings hold two tiles plus a mirrored
+// margin (so a shifted 128-row window never wraps), and every hand-off is an mbarrier
+// (TMA-style expect_tx for the weights, tcgen05.commit for MMA completion).
+// Orientation of the Theano variant: see iaf_simt.cu (point reflection on load/store).
 #include <cuda_bf16.h>
 
 #include <algorithm>
@@ -33,9 +37,22 @@
 
 #include "iaf_tc.h"
 
-#define TC_THREADS 256
+#define TC_WORKERS 16
+#define TC_WTHREADS (TC_WORKERS * 32)
+#define TC_THREADS (TC_WTHREADS + 32)
+#define TC_CTRL_WARP TC_WORKERS
 #define TC_TILE 128
-#define TC_SMEM_LIMIT (227 * 1024 - 1024)
+#define TC_SMEM_LIMIT (227 * 1024 - 2048)
+#define TC_ZITEMS 2  // z-window (slot, chunk) items per worker thread
+
+enum {
+  BAR_W = 0, BAR_ZFULL = 1, BAR_ZEMPTY = 2,
+  BAR_ACC_FULL = 3,    // + 2*j + b
+  BAR_ACC_EMPTY = 13,  // + 2*j + b
+  BAR_H_FULL = 23,     // + 2*j + b   (ring written by stage j)
+  BAR_H_EMPTY = 31,    // + 2*j + b
+  BAR_COUNT = 40
+};
 
 struct IafTcStage {
   const __nv_bfloat16* whi;  // global packed [K/8][N][8]
@@ -47,26 +64,30 @@ struct IafTcStage {
   int sm_whi, sm_wlo;        // smem byte offsets of the resident weight images
   int sm_in;                 // smem byte offset of this stage's input operand (hi plane set)
   int in_slots;              // slots per chunk plane of the input buffer
+  int sm_bias;               // smem byte offset of the fp32 bias (+ padw) table: [5][N]
   int tmem_col;
+  int dbl;                   // accumulator double-buffered in TMEM
 };
 
 struct IafTcParams {
   const float* z; const float* ctx;
   const float* post_mean; const float* post_logsd; const float* prior_mean; const float* prior_logsd;
   float* z_out; float* elem; float* bc_out; float* persample_out;
-  unsigned* counter;
+  float* tilepart;           // [NT][MAXS][Cred]
+  unsigned* counter;         // [B]
   IafTcStage st[IAF_MAX_STAGES];
   int n_stages;
   int B, C, H, W, Wp, SPS, HW;
-  long long S;   // total slots
+  int S;         // total slots
   int NT;        // tiles
   int MIR;       // mirrored margin (slots)
   int WIN;       // z window slots (128 + MIR)
   int RING;      // ring slots (256 + MIR)
-  int flip, nl, mode;
+  int MAXS;      // max samples intersecting one tile
+  int sm_part;   // smem byte offset of the per-tile partial-sum scratch
+  int flip, nl;
   float scale;
   int tmem_cols;
-  int elem_user;  // 1: elem is a user output; 0: internal scratch
 };
 
 // ------------------------------------------------------------------------------------------
@@ -79,6 +100,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
@@ -97,6 +121,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ void worker_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TC_WTHREADS) : "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
@@ -131,22 +156,22 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // UMMA shared-memory descriptor, SWIZZLE_NONE, K-major (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
 // canonical layout ((8,n),2):((16B,SBO),LBO): 8 rows x 16 B core matrices, SBO between 8-row groups
 // (128 B here: rows are linear at 16 B pitch), LBO between the two 8-element K chunks of one K=16 MMA.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
-  return d;                // base_offset 0, lbo_mode 0, layout_type 0 = SWIZZLE_NONE
+// Low word: start address >> 4 | (LBO >> 4) << 16.  High word: SBO >> 4 | version(1) << 14.
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
 }
+#define UMMA_DESC_HI ((128u >> 4) | (1u << 14))
+__device__ __forceinline__ uint64_t mk_desc(uint32_t lo) { return ((uint64_t)UMMA_DESC_HI << 32) | lo; }
 // Instruction descriptor (InstrDescriptor): f32 accumulate, A/B bf16, both K-major, M=128.
 __device__ __forceinline__ uint32_t umma_idesc(int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_TILE >> 4) << 24);
 }
 
+template <int NLT>
 __device__ __forceinline__ float tc_apply_nl(float v, int nl) {
+  if (NLT == IAF_NL_ELU) return v < 0.f ? __expf(v) - 1.0f : v;  // abs error ~1e-7, far inside the 1e-4 budget
   switch (nl) {
-    case IAF_NL_ELU: return v < 0.f ? expm1f(v) : v;
+    case IAF_NL_ELU: return v < 0.f ? __expf(v) - 1.0f : v;
     case IAF_NL_SOFTPLUS: return v > 0.f ? v + log1pf(expf(-v)) : log1pf(expf(v));
     case IAF_NL_RELU: return v >= 0.f ? v : 0.f;
     case IAF_NL_TANH: return tanhf(v);
@@ -161,9 +186,10 @@ __device__ __forceinline__ void split_store8(const float* v, uint8_t* hi_ptr, ui
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-    const float r0 = v[2 * i] - __low2float(hh), r1 = v[2 * i + 1] - __high2float(hh);
+    const uint32_t hb = *reinterpret_cast<const uint32_t*>(&hh);
+    const float r0 = v[2 * i] - __uint_as_float(hb << 16), r1 = v[2 * i + 1] - __uint_as_float(hb & 0xFFFF0000u);
     const __nv_bfloat162 ll = __floats2bfloat162_rn(r0, r1);
-    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+    h[i] = hb;
     l[i] = *reinterpret_cast<const uint32_t*>(&ll);
   }
   *reinterpret_cast<uint4*>(hi_ptr) = make_uint4(h[0], h[1], h[2], h[3]);
@@ -174,14 +200,14 @@ struct SlotInfo {
   int n, y, x, gp;
   bool valid;
 };
-__device__ __forceinline__ SlotInfo decode_slot(const IafTcParams& p, long long s) {
+__device__ __forceinline__ SlotInfo decode_slot(const IafTcParams& p, int s) {
   SlotInfo si;
   si.valid = false;
   si.n = 0; si.y = 0; si.x = 0; si.gp = 0;
   if (s >= p.S) return si;
-  si.n = (int)(s / p.SPS);
-  const int r = (int)(s - (long long)si.n * p.SPS);
-  si.y = r / p.Wp;
+  si.n = (int)((unsigned)s / (unsigned)p.SPS);
+  const int r = s - si.n * p.SPS;
+  si.y = (int)((unsigned)r / (unsigned)p.Wp);
   si.x = r - si.y * p.Wp;
   si.valid = (si.y < p.H) && (si.x < p.W);
   const int pix = si.y * p.W + si.x;
@@ -190,39 +216,60 @@ __device__ __forceinline__ SlotInfo decode_slot(const IafTcParams& p, long long 
 }
 
 // ------------------------------------------------------------------------------------------
-// the kernel
+// the kernel.  PADW: Theano pad-channel bias; MODE: IAF_MODE_STEP | IAF_MODE_LAYER;
+// NLT: IAF_NL_ELU for the fast elu path, -1 for the run-time switch.
 // ------------------------------------------------------------------------------------------
+template <bool PADW, int MODE, int NLT>
 __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_constant__ IafTcParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bar_w;
-  __shared__ __align__(8) uint64_t bar_mma;
+  __shared__ __align__(8) uint64_t bars[BAR_COUNT];
   __shared__ uint32_t s_tmem;
-  __shared__ int s_fin[64];
-  __shared__ int s_nfin;
-  __shared__ float s_part[TC_THREADS / 32];
-  __shared__ float s_csum[256];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nst = p.n_stages;
   const int G = gridDim.x;
   const int t0 = (int)((long long)blockIdx.x * p.NT / G);
   const int t1 = (int)((long long)(blockIdx.x + 1) * p.NT / G);
+  const int nt = t1 - t0;
+  const int s_max = nt + 2 * nst - 3;  // last period: heads on tile nt-1 at s = nt-1 + 2(nst-1)
 
-  // ---- one-time setup: TMEM, barriers, resident weights (1-D TMA bulk copies) ----
-  if (warp == 0) tmem_alloc(&s_tmem, (uint32_t)p.tmem_cols);
-  if (tid == 0) {
-    mbar_init(&bar_w, 1);
-    mbar_init(&bar_mma, 1);
-    fence_barrier_init();
-    uint32_t total = 0;
-    for (int j = 0; j < nst; ++j) total += 2u * (uint32_t)p.st[j].w_bytes;
-    mbar_expect_tx(&bar_w, total);
+  // ---- one-time setup ----
+  if (warp == TC_CTRL_WARP) {
+    tmem_alloc(&s_tmem, (uint32_t)p.tmem_cols);
+    if (lane == 0) {
+      mbar_init(&bars[BAR_W], 1);
+      mbar_init(&bars[BAR_ZFULL], TC_WORKERS);
+      mbar_init(&bars[BAR_ZEMPTY], 1);
+      for (int i = 0; i < 10; ++i) {
+        mbar_init(&bars[BAR_ACC_FULL + i], 1);
+        mbar_init(&bars[BAR_ACC_EMPTY + i], TC_WORKERS);
+      }
+      for (int i = 0; i < 8; ++i) {
+        mbar_init(&bars[BAR_H_FULL + i], TC_WORKERS);
+        mbar_init(&bars[BAR_H_EMPTY + i], 1);
+      }
+      fence_barrier_init();
+      uint32_t total = 0;
+      for (int j = 0; j < nst; ++j) total += 2u * (uint32_t)p.st[j].w_bytes;
+      mbar_expect_tx(&bars[BAR_W], total);
+      for (int j = 0; j < nst; ++j) {
+        for (int off = 0; off < p.st[j].w_bytes; off += 32768) {
+          const uint32_t n = (uint32_t)min(32768, p.st[j].w_bytes - off);
+          bulk_g2s(smem + p.st[j].sm_whi + off, reinterpret_cast<const uint8_t*>(p.st[j].whi) + off, n, &bars[BAR_W]);
+          bulk_g2s(smem + p.st[j].sm_wlo + off, reinterpret_cast<const uint8_t*>(p.st[j].wlo) + off, n, &bars[BAR_W]);
+        }
+      }
+    }
+  } else {
+    // bias (+ pad-channel) tables -> smem: [5][N] per stage (row 0 bias, rows 1..4 padw)
     for (int j = 0; j < nst; ++j) {
-      // chunks of <= 32 KB keep every bulk copy well inside the instruction's size field
-      for (int off = 0; off < p.st[j].w_bytes; off += 32768) {
-        const uint32_t n = (uint32_t)min(32768, p.st[j].w_bytes - off);
-        bulk_g2s(smem + p.st[j].sm_whi + off, reinterpret_cast<const uint8_t*>(p.st[j].whi) + off, n, &bar_w);
-        bulk_g2s(smem + p.st[j].sm_wlo + off, reinterpret_cast<const uint8_t*>(p.st[j].wlo) + off, n, &bar_w);
+      float* tb = reinterpret_cast<float*>(smem + p.st[j].sm_bias);
+      const int N = p.st[j].N;
+      for (int i = tid; i < 5 * N; i += TC_WTHREADS) {
+        float v = 0.f;
+        if (i < N) v = __ldg(p.st[j].bias + i);
+        else if (PADW) v = __ldg(p.st[j].padw + (i - N));
+        tb[i] = v;
       }
     }
   }
@@ -230,229 +277,328 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s_tmem;
-  uint32_t mma_parity = 0;
-  bool weights_ready = false;
 
-  const int shifts[IAF_NTAPS] = {0, 1, p.Wp - 1, p.Wp, p.Wp + 1};
-
-  // wavefront over the tile run: at step t, stage j handles tile t - j
-  const int t_end = t1 + nst - 1;  // exclusive bound on t: last step has the heads on tile t1-1
-  for (int t = t0; t < t_end; ++t) {
-    // ---- stage 0 operand: z window for tile t = slots [128t, 128t + WIN) ----
-    {
-      const IafTcStage& S0 = p.st[0];
-      const int nchunk = S0.cin >> 3;
-      const int plane = S0.in_slots * 16;          // bytes per chunk plane
-      const int lo_off = nchunk * plane;
-      for (int idx = tid; idx < p.WIN * nchunk; idx += TC_THREADS) {
-        const int sl = idx % p.WIN;
-        const int ch = idx / p.WIN;
-        const SlotInfo si = decode_slot(p, (long long)t * TC_TILE + sl);
-        float v[8];
-        if (si.valid) {
-          const size_t g = ((size_t)si.n * p.C + ch * 8) * p.HW + si.gp;
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = __ldg(p.z + g + (size_t)e * p.HW);
-          if (p.mode == IAF_MODE_LAYER) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e)
-              v[e] = fmaf(expf(__ldg(p.post_logsd + g + (size_t)e * p.HW)), v[e], __ldg(p.post_mean + g + (size_t)e * p.HW));
+  if (warp == TC_CTRL_WARP) {
+    // =====================================================================================
+    // control warp: one lane issues every MMA of this CTA
+    // =====================================================================================
+    if (lane == 0) {
+      mbar_wait(&bars[BAR_W], 0);
+      const int shifts[IAF_NTAPS] = {0, 1, p.Wp - 1, p.Wp, p.Wp + 1};
+      for (int s = -1; s <= s_max; ++s) {
+        for (int j = 0; j < nst; ++j) {
+          const int k = s + 1 - 2 * j;
+          if (k < 0 || k >= nt + (nst - 1 - j)) continue;
+          const IafTcStage& St = p.st[j];
+          const int b = St.dbl ? (k & 1) : 0;
+          const int use = St.dbl ? (k >> 1) : k;
+          if (j == 0) {
+            mbar_wait(&bars[BAR_ZFULL], (uint32_t)(k & 1));
+          } else {
+            mbar_wait(&bars[BAR_H_FULL + 2 * (j - 1) + (k & 1)], (uint32_t)((k >> 1) & 1));
+            mbar_wait(&bars[BAR_H_FULL + 2 * (j - 1) + ((k + 1) & 1)], (uint32_t)(((k + 1) >> 1) & 1));
           }
-        } else {
+          if (use >= 1) mbar_wait(&bars[BAR_ACC_EMPTY + 2 * j + b], (uint32_t)((use - 1) & 1));
+          tc_fence_after();
+
+          const uint32_t d_tmem = tmem_base + (uint32_t)(St.tmem_col + b * St.N);
+          const uint32_t idesc = umma_idesc(St.N);
+          const uint32_t a_plane = (uint32_t)St.in_slots * 16u;
+          const uint32_t a_base = smem_u32(smem + St.sm_in) + (uint32_t)((j == 0 ? 0 : (k & 1) * TC_TILE)) * 16u;
+          const uint32_t nchunk = (uint32_t)(St.cin >> 3);
+          const uint32_t b_plane = (uint32_t)St.N * 16u;
+          // descriptor low words; every step below is a plain add in units of 16 B
+          const uint32_t ah0 = umma_desc_lo(a_base, a_plane);
+          const uint32_t al0 = umma_desc_lo(a_base + nchunk * a_plane, a_plane);
+          uint32_t bh = umma_desc_lo(smem_u32(smem + St.sm_whi), b_plane);
+          uint32_t bl = umma_desc_lo(smem_u32(smem + St.sm_wlo), b_plane);
+          const uint32_t a_kstep = (2u * a_plane) >> 4, b_kstep = (2u * b_plane) >> 4;
+          const int nks = St.cin >> 4;
+          uint32_t acc = 0;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = 0.f;
+          for (int tp = 0; tp < IAF_NTAPS; ++tp) {
+            uint32_t ah = ah0 + (uint32_t)shifts[tp], al = al0 + (uint32_t)shifts[tp];
+            for (int ks = 0; ks < nks; ++ks) {
+              umma_bf16(d_tmem, mk_desc(al), mk_desc(bh), idesc, acc);  // lo * hi
+              acc = 1;
+              umma_bf16(d_tmem, mk_desc(ah), mk_desc(bl), idesc, acc);  // hi * lo
+              umma_bf16(d_tmem, mk_desc(ah), mk_desc(bh), idesc, acc);  // hi * hi
+              ah += a_kstep; al += a_kstep; bh += b_kstep; bl += b_kstep;
+            }
+          }
+          umma_commit(&bars[BAR_ACC_FULL + 2 * j + b]);
+          if (j == 0) umma_commit(&bars[BAR_ZEMPTY]);
+          else umma_commit(&bars[BAR_H_EMPTY + 2 * (j - 1) + (k & 1)]);
         }
-        uint8_t* dst = smem + S0.sm_in + ch * plane + sl * 16;
-        split_store8(v, dst, dst + lo_off);
       }
     }
-    fence_proxy_async();
-    __syncthreads();
+    __syncwarp();
+  } else {
+    // =====================================================================================
+    // worker warps: z loader + epilogues.  TMEM lane quadrant = warp % 4; the 4 warps of a
+    // quadrant split the accumulator columns in groups of 16.
+    // =====================================================================================
+    const int q = warp & 3, cg = warp >> 2;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    float* s_part = reinterpret_cast<float*>(smem + p.sm_part);
+    const int nch0 = p.st[0].cin >> 3;
+    const int n_zitems = p.WIN * nch0;
 
-    for (int j = 0; j < nst; ++j) {
-      const int u = t - j;  // tile of stage j
-      const bool last = (j == nst - 1);
-      // stage j is needed for tiles [t0, t1 + (nst-1-j))
-      if (u < t0 || u >= t1 + (nst - 1 - j)) continue;
-      const IafTcStage& St = p.st[j];
-      const uint32_t d_tmem = tmem_base + (uint32_t)St.tmem_col;
-
-      // ---- MMA issue: one thread; the rest of its warp parks at __syncwarp so that no lane of the
-      //      issuing warp sits in mbarrier.try_wait (which suspends the whole warp) meanwhile ----
-      if (warp == 0) {
-       if (lane == 0) {
-        if (!weights_ready) mbar_wait(&bar_w, 0);
-        tc_fence_after();
-        const uint32_t idesc = umma_idesc(St.N);
-        const uint32_t a_plane = (uint32_t)St.in_slots * 16u;
-        const uint32_t a_hi = smem_u32(smem + St.sm_in) + (uint32_t)((j == 0 ? 0 : (u & 1) * TC_TILE)) * 16u;
-        const uint32_t a_lo = a_hi + (uint32_t)(St.cin >> 3) * a_plane;
-        const uint32_t b_hi = smem_u32(smem + St.sm_whi), b_lo = smem_u32(smem + St.sm_wlo);
-        const uint32_t b_plane = (uint32_t)St.N * 16u;
-        uint32_t acc = 0;
-        for (int tp = 0; tp < IAF_NTAPS; ++tp) {
-          for (int ks = 0; ks < (St.cin >> 4); ++ks) {
-            const uint32_t a_off = (uint32_t)shifts[tp] * 16u + (uint32_t)(ks * 2) * a_plane;
-            const uint32_t b_off = (uint32_t)(tp * (St.cin >> 3) + ks * 2) * b_plane;
-            const uint64_t dah = umma_desc(a_hi + a_off, a_plane, 128), dal = umma_desc(a_lo + a_off, a_plane, 128);
-            const uint64_t dbh = umma_desc(b_hi + b_off, b_plane, 128), dbl = umma_desc(b_lo + b_off, b_plane, 128);
-            umma_bf16(d_tmem, dal, dbh, idesc, acc);  // lo * hi
-            acc = 1;
-            umma_bf16(d_tmem, dah, dbl, idesc, acc);  // hi * lo
-            umma_bf16(d_tmem, dah, dbh, idesc, acc);  // hi * hi
-          }
-        }
-        umma_commit(&bar_mma);
-       }
-       __syncwarp();
-      }
-      weights_ready = true;
-      mbar_wait(&bar_mma, mma_parity);
-      mma_parity ^= 1u;
-      tc_fence_after();
-
-      // ---- epilogue: thread == TMEM lane == slot; warps w and w+4 split the columns ----
-      const int q = warp & 3, hsel = warp >> 2;
-      const int sl = q * 32 + lane;
-      const long long s = (long long)u * TC_TILE + sl;
-      const SlotInfo si = decode_slot(p, s);
-      const bool bx0 = (si.x == 0), bxW = (si.x == p.W - 1), byH = (si.y == p.H - 1);
-      const int ncol_half = St.N >> 1;
-      const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)St.tmem_col;
-
-      if (!last) {
-        const IafTcStage& Nx = p.st[j + 1];
-        const int plane = Nx.in_slots * 16;
-        const int lo_off = (St.N >> 3) * plane;
-        const int rpos = (u & 1) * TC_TILE + sl;
-        uint8_t* obase = smem + Nx.sm_in + rpos * 16;
-        const bool mirror = ((u & 1) == 0) && (sl < p.MIR);
-        for (int c0 = hsel * ncol_half; c0 < (hsel + 1) * ncol_half; c0 += 16) {
-          uint32_t r[16];
-          tmem_ld16(t_lane + (uint32_t)c0, r);
-          float cx[16];
-          if (j == 0 && si.valid) {
-            const float* cp = p.ctx + ((size_t)si.n * St.N + c0) * p.HW + si.gp;
+    for (int s = -1; s <= s_max; ++s) {
+      // ------------------------------ L(s+1): z window of stage-0 tile s+1 ------------------
+      const int kz = s + 1;
+      if (kz < nt + nst - 1) {
+        const IafTcStage& S0 = p.st[0];
+        const int plane = S0.in_slots * 16;
+        const int lo_off = nch0 * plane;
+        float v[TC_ZITEMS][8];
+        int dsto[TC_ZITEMS];
 #pragma unroll
-            for (int e = 0; e < 16; ++e) cx[e] = __ldg(cp + (size_t)e * p.HW);
-          } else {
+        for (int it = 0; it < TC_ZITEMS; ++it) {
+          const int idx = tid + it * TC_WTHREADS;
+          dsto[it] = -1;
+          if (idx < n_zitems) {
+            const int ch = idx / p.WIN;
+            const int sl = idx - ch * p.WIN;
+            dsto[it] = ch * plane + sl * 16;
+            const SlotInfo si = decode_slot(p, (t0 + kz) * TC_TILE + sl);
+            if (si.valid) {
+              const size_t g = ((size_t)si.n * p.C + ch * 8) * p.HW + si.gp;
 #pragma unroll
-            for (int e = 0; e < 16; ++e) cx[e] = 0.f;
-          }
-          tmem_ld_wait();
-          float v[16];
+              for (int e = 0; e < 8; ++e) v[it][e] = __ldg(p.z + g + (size_t)e * p.HW);
+              if (MODE == IAF_MODE_LAYER) {  // z0 = mean + exp(logsd) * eps   (tf_train.py:57, distributions.py:20)
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            float a = __uint_as_float(r[e]) + __ldg(St.bias + c0 + e) + cx[e];
-            if (St.padw) {
-              if (bxW) a += __ldg(St.padw + c0 + e);
-              if (byH || bx0) a += __ldg(St.padw + St.N + c0 + e);
-              if (byH) a += __ldg(St.padw + 2 * St.N + c0 + e);
-              if (byH || bxW) a += __ldg(St.padw + 3 * St.N + c0 + e);
-            }
-            v[e] = si.valid ? tc_apply_nl(a, p.nl) : 0.f;
-          }
-#pragma unroll
-          for (int hch = 0; hch < 2; ++hch) {
-            uint8_t* dst = obase + ((c0 >> 3) + hch) * plane;
-            split_store8(v + 8 * hch, dst, dst + lo_off);
-            if (mirror) split_store8(v + 8 * hch, dst + 2 * TC_TILE * 16, dst + 2 * TC_TILE * 16 + lo_off);
-          }
-        }
-      } else {
-        // heads: columns come in groups of 16 = (m x 8, s x 8) for 8 consecutive channels
-        for (int c0 = hsel * ncol_half; c0 < (hsel + 1) * ncol_half; c0 += 16) {
-          uint32_t r[16];
-          tmem_ld16(t_lane + (uint32_t)c0, r);
-          const int ch0 = c0 >> 1;
-          float zv[8];
-          size_t g = 0;
-          if (si.valid) {
-            g = ((size_t)si.n * p.C + ch0) * p.HW + si.gp;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) zv[e] = __ldg(p.z + g + (size_t)e * p.HW);
-            if (p.mode == IAF_MODE_LAYER) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e)
-                zv[e] = fmaf(expf(__ldg(p.post_logsd + g + (size_t)e * p.HW)), zv[e], __ldg(p.post_mean + g + (size_t)e * p.HW));
-            }
-          }
-          tmem_ld_wait();
-          if (si.valid) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              float m = __uint_as_float(r[e]) + __ldg(St.bias + c0 + e);
-              float sv = __uint_as_float(r[8 + e]) + __ldg(St.bias + c0 + 8 + e);
-              if (St.padw) {
-                if (bxW) { m += __ldg(St.padw + c0 + e); sv += __ldg(St.padw + c0 + 8 + e); }
-                if (byH || bx0) { m += __ldg(St.padw + St.N + c0 + e); sv += __ldg(St.padw + St.N + c0 + 8 + e); }
-                if (byH) { m += __ldg(St.padw + 2 * St.N + c0 + e); sv += __ldg(St.padw + 2 * St.N + c0 + 8 + e); }
-                if (byH || bxW) { m += __ldg(St.padw + 3 * St.N + c0 + e); sv += __ldg(St.padw + 3 * St.N + c0 + 8 + e); }
+                for (int e = 0; e < 8; ++e)
+                  v[it][e] = fmaf(__expf(__ldg(p.post_logsd + g + (size_t)e * p.HW)), v[it][e],
+                                  __ldg(p.post_mean + g + (size_t)e * p.HW));
               }
-              const float arw_mean = p.scale * m, arw_logsd = p.scale * sv;  // models.py:282-285
-              const float zn = (zv[e] - arw_mean) / expf(arw_logsd);
-              const size_t ge = g + (size_t)e * p.HW;
-              p.z_out[ge] = zn;
-              float outv = arw_logsd;
-              if (p.mode == IAF_MODE_LAYER) {
-                const float eps = __ldg(p.z + ge);
-                const float logqs = -0.9189385332046727f - __ldg(p.post_logsd + ge) - 0.5f * eps * eps + arw_logsd;
-                const float pl = __ldg(p.prior_logsd + ge);
-                const float d = zn - __ldg(p.prior_mean + ge);
-                const float logps = -0.9189385332046727f - pl - 0.5f * d * d * expf(-2.0f * pl);
-                outv = logqs - logps;
-              }
-              p.elem[ge] = outv;
-            }
-          }
-        }
-      }
-      tc_fence_before();
-      fence_proxy_async();
-      if (last) __threadfence();
-      __syncthreads();
-      tc_fence_after();
-
-      // ---- per-sample reductions: the CTA that completes a sample's last tile reduces it ----
-      if (last && (p.persample_out || p.bc_out)) {
-        const long long s_lo = (long long)u * TC_TILE;
-        const int n_first = (int)(s_lo / p.SPS);
-        const int n_last = (int)min((long long)p.B - 1, (s_lo + TC_TILE - 1) / p.SPS);
-        if (tid == 0) s_nfin = 0;
-        __syncthreads();
-        if (tid <= n_last - n_first) {
-          const int n = n_first + tid;
-          const long long a = (long long)n * p.SPS, b = a + p.SPS - 1;
-          const unsigned expected = (unsigned)(b / TC_TILE - a / TC_TILE + 1);
-          if (atomicAdd(p.counter + n, 1u) == expected - 1u) {
-            p.counter[n] = 0u;
-            s_fin[atomicAdd(&s_nfin, 1)] = n;
-          }
-        }
-        __syncthreads();
-        const int nfin = s_nfin;
-        if (nfin > 0) {
-          __threadfence();
-          // order the finished samples so the work below does not depend on arrival order
-          for (int f = 0; f < nfin; ++f) {
-            const int n = s_fin[f];
-            for (int c = warp; c < p.C; c += TC_THREADS / 32) {
-              const float* src = p.elem + ((size_t)n * p.C + c) * p.HW;
-              float acc = 0.f;
-              for (int i = lane; i < p.HW; i += 32) acc += __ldcg(src + i);
+            } else {
 #pragma unroll
-              for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-              if (lane == 0) s_csum[c] = acc;
+              for (int e = 0; e < 8; ++e) v[it][e] = 0.f;
             }
-            __syncthreads();
-            if (p.bc_out)
-              for (int c = tid; c < p.C; c += TC_THREADS) p.bc_out[(size_t)n * p.C + c] = s_csum[c];
-            if (tid == 0 && p.persample_out) {
+          }
+        }
+        if (kz >= 1) mbar_wait(&bars[BAR_ZEMPTY], (uint32_t)((kz - 1) & 1));  // M0(kz-1) has drained the window
+#pragma unroll
+        for (int it = 0; it < TC_ZITEMS; ++it) {
+          if (dsto[it] >= 0) {
+            uint8_t* dst = smem + S0.sm_in + dsto[it];
+            split_store8(v[it], dst, dst + lo_off);
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[BAR_ZFULL]);
+      }
+
+      // ------------------------------ E_j(s - 2j) ---------------------------------------------
+      for (int j = 0; j < nst; ++j) {
+        const int k = s - 2 * j;
+        if (k < 0 || k >= nt + (nst - 1 - j)) continue;
+        const IafTcStage& St = p.st[j];
+        const bool last = (j == nst - 1);
+        const int b = St.dbl ? (k & 1) : 0;
+        const int use = St.dbl ? (k >> 1) : k;
+        const int u = t0 + k;
+        const int sl = q * 32 + lane;
+        const SlotInfo si = decode_slot(p, u * TC_TILE + sl);
+        const bool bx0 = (si.x == 0), bxW = (si.x == p.W - 1), byH = (si.y == p.H - 1);
+        const float* tb = reinterpret_cast<const float*>(smem + St.sm_bias);
+        const uint32_t t_acc = t_lane + (uint32_t)(St.tmem_col + b * St.N);
+        const int ngroups = St.N >> 4;
+
+        if (!last) {
+          const IafTcStage& Nx = p.st[j + 1];
+          const int plane = Nx.in_slots * 16;
+          const int lo_off = (St.N >> 3) * plane;
+          uint8_t* obase = smem + Nx.sm_in + ((k & 1) * TC_TILE + sl) * 16;
+          const bool mirror = ((k & 1) == 0) && (sl < p.MIR);
+          bool waited = false;
+          for (int g = cg; g < ngroups; g += 4) {
+            const int c0 = g * 16;
+            float cx[16];
+            if (j == 0 && si.valid) {  // += context   (ar.py:402 / layers.py:163)
+              const float* cp = p.ctx + ((size_t)si.n * St.N + c0) * p.HW + si.gp;
+#pragma unroll
+              for (int e = 0; e < 16; ++e) cx[e] = __ldg(cp + (size_t)e * p.HW);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) cx[e] = 0.f;
+            }
+            if (!waited) {
+              mbar_wait(&bars[BAR_ACC_FULL + 2 * j + b], (uint32_t)(use & 1));
+              tc_fence_after();
+              // ring slot k&1 was last read by M_{j+1}(k-2)
+              if (k >= 2) mbar_wait(&bars[BAR_H_EMPTY + 2 * j + (k & 1)], (uint32_t)(((k >> 1) - 1) & 1));
+              waited = true;
+            }
+            uint32_t r[16];
+            tmem_ld16(t_acc + (uint32_t)c0, r);
+            tmem_ld_wait();
+            float v[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              float a = __uint_as_float(r[e]) + tb[c0 + e] + cx[e];
+              if (PADW) {  // pad channel = 1 where the tap falls outside the image (conv.py:77-83)
+                if (bxW) a += tb[St.N + c0 + e];
+                if (byH || bx0) a += tb[2 * St.N + c0 + e];
+                if (byH) a += tb[3 * St.N + c0 + e];
+                if (byH || bxW) a += tb[4 * St.N + c0 + e];
+              }
+              v[e] = si.valid ? tc_apply_nl<NLT>(a, p.nl) : 0.f;
+            }
+#pragma unroll
+            for (int hch = 0; hch < 2; ++hch) {
+              uint8_t* dst = obase + ((c0 >> 3) + hch) * plane;
+              split_store8(v + 8 * hch, dst, dst + lo_off);
+              if (mirror) split_store8(v + 8 * hch, dst + 2 * TC_TILE * 16, dst + 2 * TC_TILE * 16 + lo_off);
+            }
+          }
+          if (!waited) {  // a warp with no column group still takes part in the hand-off
+            mbar_wait(&bars[BAR_ACC_FULL + 2 * j + b], (uint32_t)(use & 1));
+          }
+          tc_fence_before();
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(&bars[BAR_ACC_EMPTY + 2 * j + b]);
+            mbar_arrive(&bars[BAR_H_FULL + 2 * j + (k & 1)]);
+          }
+        } else {
+          // ---------------- heads: columns in groups of 16 = (m x 8, s x 8) of 8 channels --------------
+          constexpr int NRED = (MODE == IAF_MODE_LAYER) ? 8 : 1;
+          float red[NRED];
+#pragma unroll
+          for (int i = 0; i < NRED; ++i) red[i] = 0.f;
+          const int tile_s0 = u * TC_TILE;
+          const int n_first = (int)((unsigned)tile_s0 / (unsigned)p.SPS);
+          const int n_last = min(p.B - 1, (int)((unsigned)(tile_s0 + TC_TILE - 1) / (unsigned)p.SPS));
+          const int ns = (tile_s0 < p.S) ? (n_last - n_first + 1) : 0;
+          bool waited = false;
+          for (int g = cg; g < ngroups; g += 4) {
+            const int c0 = g * 16;
+            const int ch0 = g * 8;
+            float zv[8];
+            size_t gi = 0;
+            if (si.valid) {
+              gi = ((size_t)si.n * p.C + ch0) * p.HW + si.gp;
+#pragma unroll
+              for (int e = 0; e < 8; ++e) zv[e] = __ldg(p.z + gi + (size_t)e * p.HW);
+            }
+            if (!waited) {
+              mbar_wait(&bars[BAR_ACC_FULL + 2 * j + b], (uint32_t)(use & 1));
+              tc_fence_after();
+              waited = true;
+            }
+            uint32_t r[16];
+            tmem_ld16(t_acc + (uint32_t)c0, r);
+            tmem_ld_wait();
+            if (MODE == IAF_MODE_LAYER) {
+#pragma unroll
+              for (int i = 0; i < NRED; ++i) red[i] = 0.f;
+            }
+            if (si.valid) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                float m = __uint_as_float(r[e]) + tb[c0 + e];
+                float sv = __uint_as_float(r[8 + e]) + tb[c0 + 8 + e];
+                if (PADW) {
+                  if (bxW) { m += tb[St.N + c0 + e]; sv += tb[St.N + c0 + 8 + e]; }
+                  if (byH || bx0) { m += tb[2 * St.N + c0 + e]; sv += tb[2 * St.N + c0 + 8 + e]; }
+                  if (byH) { m += tb[3 * St.N + c0 + e]; sv += tb[3 * St.N + c0 + 8 + e]; }
+                  if (byH || bxW) { m += tb[4 * St.N + c0 + e]; sv += tb[4 * St.N + c0 + 8 + e]; }
+                }
+                const float arw_mean = p.scale * m, arw_logsd = p.scale * sv;  // models.py:282-285
+                const size_t ge = gi + (size_t)e * p.HW;
+                float z0 = zv[e];
+                float eps = 0.f, pls = 0.f;
+                if (MODE == IAF_MODE_LAYER) {
+                  eps = z0;
+                  pls = __ldg(p.post_logsd + ge);
+                  z0 = fmaf(__expf(pls), eps, __ldg(p.post_mean + ge));
+                }
+                const float zn = (z0 - arw_mean) * __expf(-arw_logsd);
+                p.z_out[ge] = zn;
+                if (MODE == IAF_MODE_STEP) {
+                  if (p.elem) p.elem[ge] = arw_logsd;
+                  red[0] += arw_logsd;
+                } else {
+                  // logqs of the pre-flow sample + arw_logsd, prior logps at z'  (tf_train.py:68-75)
+                  const float logqs = -0.9189385332046727f - pls - 0.5f * eps * eps + arw_logsd;
+                  const float pl = __ldg(p.prior_logsd + ge);
+                  const float d = zn - __ldg(p.prior_mean + ge);
+                  const float logps = -0.9189385332046727f - pl - 0.5f * d * d * __expf(-2.0f * pl);
+                  const float kl = logqs - logps;
+                  if (p.elem) p.elem[ge] = kl;
+                  red[e] = kl;
+                }
+              }
+            }
+            if (MODE == IAF_MODE_LAYER) {
+              // per-(sample, channel) sums over this warp's 32 slots, fixed butterfly order
+              for (int nl_ = 0; nl_ < ns; ++nl_) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  float x = (si.valid && si.n == n_first + nl_) ? red[e] : 0.f;
+#pragma unroll
+                  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+                  if (lane == 0) s_part[(q * p.MAXS + nl_) * p.C + ch0 + e] = x;
+                }
+              }
+            }
+          }
+          if (!waited) mbar_wait(&bars[BAR_ACC_FULL + 2 * j + b], (uint32_t)(use & 1));
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars[BAR_ACC_EMPTY + 2 * j + b]);
+
+          // ---------------- deterministic per-sample reductions ----------------
+          if (p.persample_out || p.bc_out) {
+            if (MODE == IAF_MODE_STEP) {
+              for (int nl_ = 0; nl_ < ns; ++nl_) {
+                float x = (si.valid && si.n == n_first + nl_) ? red[0] : 0.f;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+                if (lane == 0) s_part[warp * p.MAXS + nl_] = x;
+              }
+            }
+            worker_bar_sync();
+            constexpr bool LAY = (MODE == IAF_MODE_LAYER);
+            const int cred = LAY ? p.C : 1;
+            // tile partials -> global, fixed summation order
+            for (int i = tid; i < ns * cred; i += TC_WTHREADS) {
               float tot = 0.f;
-              for (int c = 0; c < p.C; ++c) tot += s_csum[c];
-              p.persample_out[n] = (p.mode == IAF_MODE_STEP) ? -tot : tot;
+              if (LAY) {
+                const int nl_ = i / p.C, c = i - nl_ * p.C;
+                for (int qq = 0; qq < 4; ++qq) tot += s_part[(qq * p.MAXS + nl_) * p.C + c];
+              } else {
+                for (int w = 0; w < TC_WORKERS; ++w) tot += s_part[w * p.MAXS + i];
+              }
+              p.tilepart[((size_t)u * p.MAXS) * cred + i] = tot;
             }
-            __syncthreads();
+            __threadfence();
+            worker_bar_sync();
+            if (tid < ns) {
+              const int n = n_first + tid;
+              const int a = n * p.SPS, bb = a + p.SPS - 1;
+              const int ta = a / TC_TILE, tbk = bb / TC_TILE;
+              const unsigned expected = (unsigned)(tbk - ta + 1);
+              if (atomicAdd(p.counter + n, 1u) == expected - 1u) {
+                __threadfence();
+                p.counter[n] = 0u;  // ready for the next launch
+                float cost = 0.f;
+                for (int c = 0; c < cred; ++c) {
+                  float tot = 0.f;
+                  for (int tt = ta; tt <= tbk; ++tt) {
+                    const int nf = (int)((unsigned)(tt * TC_TILE) / (unsigned)p.SPS);
+                    tot += __ldcg(p.tilepart + ((size_t)tt * p.MAXS + (n - nf)) * cred + c);
+                  }
+                  if (LAY && p.bc_out) p.bc_out[(size_t)n * p.C + c] = tot;
+                  cost += tot;
+                }
+                if (p.persample_out) p.persample_out[n] = LAY ? cost : -cost;  // logdet = -sum(arw_logsd)
+              }
+            }
           }
         }
       }
@@ -461,8 +607,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
-  (void)s_part;
+  if (warp == TC_CTRL_WARP) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -555,14 +700,26 @@ struct IafTcPlan {
   __nv_bfloat16* wlo[IAF_MAX_STAGES];
   float* bias[IAF_MAX_STAGES];
   float* padw[IAF_MAX_STAGES];
-  int sm_whi[IAF_MAX_STAGES], sm_wlo[IAF_MAX_STAGES], sm_in[IAF_MAX_STAGES], in_slots[IAF_MAX_STAGES], tmem_col[IAF_MAX_STAGES];
-  int MIR, WIN, RING, tmem_cols;
+  int sm_whi[IAF_MAX_STAGES], sm_wlo[IAF_MAX_STAGES], sm_in[IAF_MAX_STAGES], in_slots[IAF_MAX_STAGES];
+  int sm_bias[IAF_MAX_STAGES], tmem_col[IAF_MAX_STAGES], dbl[IAF_MAX_STAGES];
+  int MIR, WIN, RING, MAXS, sm_part, tmem_cols;
+  bool layer_ok;             // the per-(sample,channel) scratch of the fused-layer mode fits
   size_t smem;
   unsigned* counter;
-  float* elem_scratch;
+  float* tilepart;
   int scratch_B;
   int num_sms;
 };
+
+typedef void (*TcKernel)(const IafTcParams);
+static TcKernel tc_kernel_for(bool padw, int mode, bool elu) {
+  if (mode == IAF_MODE_STEP) {
+    if (padw) return elu ? iaf_tc_kernel<true, IAF_MODE_STEP, IAF_NL_ELU> : iaf_tc_kernel<true, IAF_MODE_STEP, -1>;
+    return elu ? iaf_tc_kernel<false, IAF_MODE_STEP, IAF_NL_ELU> : iaf_tc_kernel<false, IAF_MODE_STEP, -1>;
+  }
+  if (padw) return elu ? iaf_tc_kernel<true, IAF_MODE_LAYER, IAF_NL_ELU> : iaf_tc_kernel<true, IAF_MODE_LAYER, -1>;
+  return elu ? iaf_tc_kernel<false, IAF_MODE_LAYER, IAF_NL_ELU> : iaf_tc_kernel<false, IAF_MODE_LAYER, -1>;
+}
 
 static int tc_round_up(int a, int b) { return (a + b - 1) / b * b; }
 
@@ -570,16 +727,19 @@ static bool tc_layout(const iaf_desc_t* d, IafTcPlan* pl) {
   if (d->n_hidden < 1 || d->n_heads != 2 || d->head[0] != d->n_z || d->head[1] != d->n_z) return false;
   if (d->n_z % 16 != 0 || 2 * d->n_z > 256) return false;
   for (int i = 0; i < d->n_hidden; ++i)
-    if (d->hidden[i] % 32 != 0 || d->hidden[i] > 256) return false;
+    if (d->hidden[i] % 16 != 0 || d->hidden[i] > 256) return false;
   const int nst = d->n_hidden + 1;
   const int Wp = d->W + 1;
+  const int SPS = (d->H + 1) * Wp;
   const int MIR = tc_round_up(Wp + 1, 8);  // largest tap shift, rounded
   if (MIR > TC_TILE) return false;
   IafTcPlan tmp;
   IafTcPlan* q = pl ? pl : &tmp;
   q->n_stages = nst;
   q->MIR = MIR; q->WIN = TC_TILE + MIR; q->RING = 2 * TC_TILE + MIR;
-  int off = 0, col = 0, prev = d->n_z;
+  q->MAXS = (TC_TILE - 1) / SPS + 2;
+  if ((d->n_z / 8) * q->WIN > TC_ZITEMS * TC_WTHREADS) return false;
+  int off = 0, prev = d->n_z;
   for (int j = 0; j < nst; ++j) {
     q->cin[j] = prev;
     q->N[j] = (j < d->n_hidden) ? d->hidden[j] : 2 * d->n_z;
@@ -587,16 +747,31 @@ static bool tc_layout(const iaf_desc_t* d, IafTcPlan* pl) {
     const int wb = q->K[j] * q->N[j] * 2;
     q->sm_whi[j] = off; off += wb;
     q->sm_wlo[j] = off; off += wb;
-    q->tmem_col[j] = col; col += q->N[j];
     prev = q->N[j];
   }
-  prev = d->n_z;
   for (int j = 0; j < nst; ++j) {
     q->in_slots[j] = (j == 0) ? q->WIN : q->RING;
     q->sm_in[j] = off;
     off += 2 * (q->cin[j] / 8) * q->in_slots[j] * 16;  // hi + lo plane sets
   }
-  if (col > 512) return false;
+  for (int j = 0; j < nst; ++j) {
+    q->sm_bias[j] = off;
+    off += 5 * q->N[j] * 4;
+  }
+  off = tc_round_up(off, 16);
+  q->sm_part = off;
+  const int part_step = TC_WORKERS * q->MAXS * 4;
+  const int part_layer = 4 * q->MAXS * d->n_z * 4;
+  q->layer_ok = (off + std::max(part_step, part_layer)) <= TC_SMEM_LIMIT;
+  off += q->layer_ok ? std::max(part_step, part_layer) : part_step;
+  // TMEM: double-buffer as many accumulators as fit in 512 columns, the heads first
+  int cols = 0;
+  for (int j = 0; j < nst; ++j) { q->dbl[j] = 0; cols += q->N[j]; }
+  if (cols > 512) return false;
+  for (int j = nst - 1; j >= 0; --j)
+    if (cols + q->N[j] <= 512) { q->dbl[j] = 1; cols += q->N[j]; }
+  int col = 0;
+  for (int j = 0; j < nst; ++j) { q->tmem_col[j] = col; col += q->N[j] * (1 + q->dbl[j]); }
   int tc = 32;
   while (tc < col) tc *= 2;
   q->tmem_cols = tc;
@@ -626,9 +801,12 @@ int iaf_tc_plan_create(IafTcPlan** out, const iaf_desc_t* d) {
       return IAF_ERR_CUDA;
     }
   }
-  if (cudaFuncSetAttribute(iaf_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem) != cudaSuccess) {
-    iaf_tc_plan_destroy(pl);
-    return IAF_ERR_CUDA;
+  for (int a = 0; a < 8; ++a) {
+    TcKernel k = tc_kernel_for(a & 1, (a & 2) ? IAF_MODE_LAYER : IAF_MODE_STEP, a & 4);
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem) != cudaSuccess) {
+      iaf_tc_plan_destroy(pl);
+      return IAF_ERR_CUDA;
+    }
   }
   *out = pl;
   return IAF_OK;
@@ -643,10 +821,9 @@ void iaf_tc_plan_destroy(IafTcPlan* pl) {
     if (pl->padw[j]) cudaFree(pl->padw[j]);
   }
   if (pl->counter) cudaFree(pl->counter);
-  if (pl->elem_scratch) cudaFree(pl->elem_scratch);
+  if (pl->tilepart) cudaFree(pl->tilepart);
   delete pl;
 }
-
 int iaf_tc_pack(IafTcPlan* pl, const float* const* w, const float* const* scale, const float* const* bias,
                 cudaStream_t stream) {
   const iaf_desc_t& d = pl->d;
@@ -680,16 +857,22 @@ int iaf_tc_pack(IafTcPlan* pl, const float* const* w, const float* const* scale,
   return cudaGetLastError() == cudaSuccess ? IAF_OK : IAF_ERR_CUDA;
 }
 
+bool iaf_tc_mode_supported(const IafTcPlan* pl, int mode) { return mode == IAF_MODE_STEP || (mode == IAF_MODE_LAYER && pl->layer_ok); }
+
 int iaf_tc_run(IafTcPlan* pl, const IafTcArgs* a, cudaStream_t stream, int* n_launches) {
   const iaf_desc_t& d = pl->d;
   const int B = a->B;
+  const int SPS = (d.H + 1) * (d.W + 1);
+  if ((long long)B * SPS + TC_TILE >= (1LL << 31)) return IAF_ERR_UNSUPPORTED;
+  const int S = B * SPS;
+  const int NT = (S + TC_TILE - 1) / TC_TILE;
   if (B > pl->scratch_B) {
     if (pl->counter) cudaFree(pl->counter);
-    if (pl->elem_scratch) cudaFree(pl->elem_scratch);
-    pl->counter = nullptr; pl->elem_scratch = nullptr; pl->scratch_B = 0;
+    if (pl->tilepart) cudaFree(pl->tilepart);
+    pl->counter = nullptr; pl->tilepart = nullptr; pl->scratch_B = 0;
     if (cudaMalloc(&pl->counter, sizeof(unsigned) * (size_t)B) != cudaSuccess) return IAF_ERR_CUDA;
     if (cudaMemset(pl->counter, 0, sizeof(unsigned) * (size_t)B) != cudaSuccess) return IAF_ERR_CUDA;
-    if (cudaMalloc(&pl->elem_scratch, sizeof(float) * (size_t)B * d.n_z * d.H * d.W) != cudaSuccess) return IAF_ERR_CUDA;
+    if (cudaMalloc(&pl->tilepart, sizeof(float) * (size_t)NT * pl->MAXS * d.n_z) != cudaSuccess) return IAF_ERR_CUDA;
     pl->scratch_B = B;
   }
   IafTcParams p;
@@ -697,29 +880,30 @@ int iaf_tc_run(IafTcPlan* pl, const IafTcArgs* a, cudaStream_t stream, int* n_la
   p.z = a->z; p.ctx = a->ctx; p.post_mean = a->post_mean; p.post_logsd = a->post_logsd;
   p.prior_mean = a->prior_mean; p.prior_logsd = a->prior_logsd;
   p.z_out = a->z_out;
-  p.elem = a->elem_out ? a->elem_out : pl->elem_scratch;
-  p.elem_user = a->elem_out ? 1 : 0;
+  p.elem = a->elem_out;
   p.bc_out = a->bc_out; p.persample_out = a->persample_out;
+  p.tilepart = pl->tilepart;
   p.counter = pl->counter;
   p.n_stages = pl->n_stages;
   for (int j = 0; j < pl->n_stages; ++j) {
-    IafTcStage& S = p.st[j];
-    S.whi = pl->whi[j]; S.wlo = pl->wlo[j]; S.bias = pl->bias[j];
-    S.padw = d.variant == IAF_VARIANT_THEANO ? pl->padw[j] : nullptr;
-    S.cin = pl->cin[j]; S.N = pl->N[j]; S.K = pl->K[j];
-    S.w_bytes = pl->K[j] * pl->N[j] * 2;
-    S.sm_whi = pl->sm_whi[j]; S.sm_wlo = pl->sm_wlo[j]; S.sm_in = pl->sm_in[j];
-    S.in_slots = pl->in_slots[j]; S.tmem_col = pl->tmem_col[j];
+    IafTcStage& S_ = p.st[j];
+    S_.whi = pl->whi[j]; S_.wlo = pl->wlo[j]; S_.bias = pl->bias[j];
+    S_.padw = pl->padw[j];
+    S_.cin = pl->cin[j]; S_.N = pl->N[j]; S_.K = pl->K[j];
+    S_.w_bytes = pl->K[j] * pl->N[j] * 2;
+    S_.sm_whi = pl->sm_whi[j]; S_.sm_wlo = pl->sm_wlo[j]; S_.sm_in = pl->sm_in[j];
+    S_.in_slots = pl->in_slots[j]; S_.sm_bias = pl->sm_bias[j];
+    S_.tmem_col = pl->tmem_col[j]; S_.dbl = pl->dbl[j];
   }
-  p.B = B; p.C = d.n_z; p.H = d.H; p.W = d.W; p.Wp = d.W + 1; p.SPS = (d.H + 1) * (d.W + 1); p.HW = d.H * d.W;
-  p.S = (long long)B * p.SPS;
-  p.NT = (int)((p.S + TC_TILE - 1) / TC_TILE);
-  p.MIR = pl->MIR; p.WIN = pl->WIN; p.RING = pl->RING;
+  p.B = B; p.C = d.n_z; p.H = d.H; p.W = d.W; p.Wp = d.W + 1; p.SPS = SPS; p.HW = d.H * d.W;
+  p.S = S; p.NT = NT;
+  p.MIR = pl->MIR; p.WIN = pl->WIN; p.RING = pl->RING; p.MAXS = pl->MAXS; p.sm_part = pl->sm_part;
   p.flip = d.variant == IAF_VARIANT_THEANO ? 1 : 0;
-  p.nl = d.nl; p.mode = a->mode; p.scale = 0.1f;
+  p.nl = d.nl; p.scale = 0.1f;
   p.tmem_cols = pl->tmem_cols;
-  const int grid = std::min(pl->num_sms, p.NT);
-  iaf_tc_kernel<<<grid, TC_THREADS, pl->smem, stream>>>(p);
+  const int grid = std::min(pl->num_sms, NT);
+  TcKernel k = tc_kernel_for(d.variant == IAF_VARIANT_THEANO, a->mode, d.nl == IAF_NL_ELU);
+  k<<<grid, TC_THREADS, pl->smem, stream>>>(p);
   if (n_launches) *n_launches = 1;
   return cudaGetLastError() == cudaSuccess ? IAF_OK : IAF_ERR_CUDA;
 }

@@ -24,4 +24,5 @@ int iaf_tc_plan_create(IafTcPlan** out, const iaf_desc_t* d);
 void iaf_tc_plan_destroy(IafTcPlan* p);
 int iaf_tc_pack(IafTcPlan* p, const float* const* w, const float* const* scale, const float* const* bias,
                 cudaStream_t stream);
+bool iaf_tc_mode_supported(const IafTcPlan* p, int mode);
 int iaf_tc_run(IafTcPlan* p, const IafTcArgs* a, cudaStream_t stream, int* n_launches);
