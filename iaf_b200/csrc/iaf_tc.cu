@@ -32,6 +32,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstring>
 #include <new>
 
@@ -43,7 +44,10 @@
 #define TC_CTRL_WARP TC_WORKERS
 #define TC_TILE 128
 #define TC_SMEM_LIMIT (227 * 1024 - 2048)
-#define TC_ZITEMS 2  // z-window (slot, chunk) items per worker thread
+#define TC_NGROUPS 1   // 1: all 16 worker warps run every phase together; 2: two ping-pong groups by tile parity
+#define TC_GWARPS (TC_WORKERS / TC_NGROUPS)
+#define TC_GTHREADS (TC_GWARPS * 32)
+#define TC_ZITEMS (TC_NGROUPS == 1 ? 2 : 3)  // z-window (slot, chunk) items per loader thread
 
 enum {
   BAR_W = 0, BAR_ZFULL = 1, BAR_ZEMPTY = 2,
@@ -51,7 +55,8 @@ enum {
   BAR_ACC_EMPTY = 13,  // + 2*j + b
   BAR_H_FULL = 23,     // + 2*j + b   (ring written by stage j)
   BAR_H_EMPTY = 31,    // + 2*j + b
-  BAR_COUNT = 40
+  BAR_PART = 40,       // + tile parity
+  BAR_COUNT = 42
 };
 
 struct IafTcStage {
@@ -88,6 +93,7 @@ struct IafTcParams {
   int flip, nl;
   float scale;
   int tmem_cols;
+  unsigned mg_sps, mg_wp, mg_win;  // magic multipliers for fast_div
 };
 
 // ------------------------------------------------------------------------------------------
@@ -120,6 +126,18 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+// one lane of a converged warp (the compiler then issues the tcgen05 ops straight from the uniform datapath)
+__device__ __forceinline__ uint32_t elect_one_sync() {
+  uint32_t pred = 0, laneid = 0;
+  asm volatile(
+      "{\n\t.reg .b32 %%rx;\n\t.reg .pred %%px;\n\t"
+      "elect.sync %%rx|%%px, %2;\n\t"
+      "@%%px mov.s32 %1, 1;\n\t"
+      "mov.s32 %0, %%rx;\n\t}"
+      : "+r"(laneid), "+r"(pred)
+      : "r"(0xFFFFFFFFu));
+  return pred;
 }
 __device__ __forceinline__ void worker_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TC_WTHREADS) : "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -167,11 +185,25 @@ __device__ __forceinline__ uint32_t umma_idesc(int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_TILE >> 4) << 24);
 }
 
+// exp via ex2.approx.ftz (2 ulp): used where 1e-7-level error is far inside the 1e-4 parity budget
+__device__ __forceinline__ float fast_exp(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  return y;
+}
+
+// floor(s / d) for 0 <= s < 2^31 with magic = floor(2^32 / d) + 1 (d >= 2): one mul-hi and a fix-up
+__device__ __forceinline__ int fast_div(int s, int d, unsigned magic) {
+  int q = (int)__umulhi((unsigned)s, magic);
+  if (s - q * d < 0) --q;
+  return q;
+}
+
 template <int NLT>
 __device__ __forceinline__ float tc_apply_nl(float v, int nl) {
-  if (NLT == IAF_NL_ELU) return v < 0.f ? __expf(v) - 1.0f : v;  // abs error ~1e-7, far inside the 1e-4 budget
+  if (NLT == IAF_NL_ELU) return v < 0.f ? fast_exp(v) - 1.0f : v;  // abs error ~1e-7, far inside the 1e-4 budget
   switch (nl) {
-    case IAF_NL_ELU: return v < 0.f ? __expf(v) - 1.0f : v;
+    case IAF_NL_ELU: return v < 0.f ? fast_exp(v) - 1.0f : v;
     case IAF_NL_SOFTPLUS: return v > 0.f ? v + log1pf(expf(-v)) : log1pf(expf(v));
     case IAF_NL_RELU: return v >= 0.f ? v : 0.f;
     case IAF_NL_TANH: return tanhf(v);
@@ -196,22 +228,47 @@ __device__ __forceinline__ void split_store8(const float* v, uint8_t* hi_ptr, ui
   *reinterpret_cast<uint4*>(lo_ptr) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// Optional in-kernel timeline (compile with -DIAF_TC_TIMELINE; development aid only): CTA 0 records
+// (tag, tile, clock) triples for the control lane and lane 0 of the first warp of each worker group.
+#ifdef IAF_TC_TIMELINE
+#define TL_MAX 128
+__device__ long long g_tl[3][TL_MAX][3];
+__device__ int g_tl_n[3];
+// events are staged in shared memory (a global counter would cost an L2 round trip per event)
+#define TL_DECL __shared__ long long s_tl[3][TL_MAX][3]; __shared__ int s_tl_n[3]; if (threadIdx.x < 3) s_tl_n[threadIdx.x] = 0;
+#define TL(role, tag, kk)                                                          \
+  do {                                                                             \
+    if (blockIdx.x == 0) {                                                         \
+      const int i_ = s_tl_n[role];                                                 \
+      if (i_ < TL_MAX) { s_tl[role][i_][0] = (tag); s_tl[role][i_][1] = (kk); s_tl[role][i_][2] = clock64(); s_tl_n[role] = i_ + 1; } \
+    }                                                                              \
+  } while (0)
+#define TL_FLUSH                                                                   \
+  if (blockIdx.x == 0 && threadIdx.x < 3) {                                        \
+    const int r_ = threadIdx.x;                                                    \
+    for (int i_ = 0; i_ < s_tl_n[r_]; ++i_)                                        \
+      for (int c_ = 0; c_ < 3; ++c_) g_tl[r_][i_][c_] = s_tl[r_][i_][c_];          \
+    g_tl_n[r_] = s_tl_n[r_];                                                       \
+  }
+#else
+#define TL_DECL
+#define TL_FLUSH
+#define TL(role, tag, kk) do { } while (0)
+#endif
+
 struct SlotInfo {
   int n, y, x, gp;
   bool valid;
 };
-__device__ __forceinline__ SlotInfo decode_slot(const IafTcParams& p, int s) {
+__device__ __forceinline__ SlotInfo decode_slot(const IafTcParams& p, int s, int HW) {
   SlotInfo si;
-  si.valid = false;
-  si.n = 0; si.y = 0; si.x = 0; si.gp = 0;
-  if (s >= p.S) return si;
-  si.n = (int)((unsigned)s / (unsigned)p.SPS);
+  si.n = fast_div(s, p.SPS, p.mg_sps);
   const int r = s - si.n * p.SPS;
-  si.y = (int)((unsigned)r / (unsigned)p.Wp);
+  si.y = fast_div(r, p.Wp, p.mg_wp);
   si.x = r - si.y * p.Wp;
-  si.valid = (si.y < p.H) && (si.x < p.W);
+  si.valid = (s < p.S) && (si.y < p.H) && (si.x < p.W);
   const int pix = si.y * p.W + si.x;
-  si.gp = p.flip ? p.HW - 1 - pix : pix;
+  si.gp = p.flip ? HW - 1 - pix : pix;
   return si;
 }
 
@@ -219,11 +276,13 @@ __device__ __forceinline__ SlotInfo decode_slot(const IafTcParams& p, int s) {
 // the kernel.  PADW: Theano pad-channel bias; MODE: IAF_MODE_STEP | IAF_MODE_LAYER;
 // NLT: IAF_NL_ELU for the fast elu path, -1 for the run-time switch.
 // ------------------------------------------------------------------------------------------
-template <bool PADW, int MODE, int NLT>
+template <bool PADW, int MODE, int NLT, int THW>
 __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_constant__ IafTcParams p) {
+  const int HW = THW ? THW : p.HW;  // compile-time plane size turns every channel stride into an immediate
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bars[BAR_COUNT];
   __shared__ uint32_t s_tmem;
+  TL_DECL
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nst = p.n_stages;
@@ -238,16 +297,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
     tmem_alloc(&s_tmem, (uint32_t)p.tmem_cols);
     if (lane == 0) {
       mbar_init(&bars[BAR_W], 1);
-      mbar_init(&bars[BAR_ZFULL], TC_WORKERS);
+      mbar_init(&bars[BAR_ZFULL], TC_GWARPS);
       mbar_init(&bars[BAR_ZEMPTY], 1);
       for (int i = 0; i < 10; ++i) {
         mbar_init(&bars[BAR_ACC_FULL + i], 1);
-        mbar_init(&bars[BAR_ACC_EMPTY + i], TC_WORKERS);
+        mbar_init(&bars[BAR_ACC_EMPTY + i], TC_GWARPS);
       }
       for (int i = 0; i < 8; ++i) {
-        mbar_init(&bars[BAR_H_FULL + i], TC_WORKERS);
+        mbar_init(&bars[BAR_H_FULL + i], TC_GWARPS);
         mbar_init(&bars[BAR_H_EMPTY + i], 1);
       }
+      mbar_init(&bars[BAR_PART], TC_GWARPS);
+      mbar_init(&bars[BAR_PART + 1], TC_GWARPS);
       fence_barrier_init();
       uint32_t total = 0;
       for (int j = 0; j < nst; ++j) total += 2u * (uint32_t)p.st[j].w_bytes;
@@ -282,7 +343,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
     // =====================================================================================
     // control warp: one lane issues every MMA of this CTA
     // =====================================================================================
-    if (lane == 0) {
+    // the whole warp walks the schedule (convergent, so addresses live in uniform registers);
+    // a single elected lane issues the MMAs and commits
+    {
       mbar_wait(&bars[BAR_W], 0);
       const int shifts[IAF_NTAPS] = {0, 1, p.Wp - 1, p.Wp, p.Wp + 1};
       for (int s = -1; s <= s_max; ++s) {
@@ -300,6 +363,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
           }
           if (use >= 1) mbar_wait(&bars[BAR_ACC_EMPTY + 2 * j + b], (uint32_t)((use - 1) & 1));
           tc_fence_after();
+          if (lane == 0) TL(0, 100 + j, k);
 
           const uint32_t d_tmem = tmem_base + (uint32_t)(St.tmem_col + b * St.N);
           const uint32_t idesc = umma_idesc(St.N);
@@ -314,6 +378,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
           uint32_t bl = umma_desc_lo(smem_u32(smem + St.sm_wlo), b_plane);
           const uint32_t a_kstep = (2u * a_plane) >> 4, b_kstep = (2u * b_plane) >> 4;
           const int nks = St.cin >> 4;
+          if (elect_one_sync()) {
           uint32_t acc = 0;
 #pragma unroll
           for (int tp = 0; tp < IAF_NTAPS; ++tp) {
@@ -329,6 +394,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
           umma_commit(&bars[BAR_ACC_FULL + 2 * j + b]);
           if (j == 0) umma_commit(&bars[BAR_ZEMPTY]);
           else umma_commit(&bars[BAR_H_EMPTY + 2 * (j - 1) + (k & 1)]);
+          TL(0, 200 + j, k);
+          }
+          __syncwarp();
         }
       }
     }
@@ -338,7 +406,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
     // worker warps: z loader + epilogues.  TMEM lane quadrant = warp % 4; the 4 warps of a
     // quadrant split the accumulator columns in groups of 16.
     // =====================================================================================
-    const int q = warp & 3, cg = warp >> 2;
+    // two ping-pong groups of 8 warps: group g runs every phase of the tiles with (k & 1) == g, so one
+    // group's load / barrier latency is covered by the other group's arithmetic
+    const int q = warp & 3, cg = (warp >> 2) % (TC_GWARPS / 4), grp = warp / TC_GWARPS, gwarp = warp % TC_GWARPS, gtid = tid % TC_GTHREADS;
+    constexpr int CGS = TC_GWARPS / 4;  // warps sharing one lane quadrant = stride over column groups
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     float* s_part = reinterpret_cast<float*>(smem + p.sm_part);
     const int nch0 = p.st[0].cin >> 3;
@@ -347,7 +418,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
     for (int s = -1; s <= s_max; ++s) {
       // ------------------------------ L(s+1): z window of stage-0 tile s+1 ------------------
       const int kz = s + 1;
-      if (kz < nt + nst - 1) {
+      if (kz < nt + nst - 1 && (TC_NGROUPS == 1 || (kz & 1) == grp)) {
         const IafTcStage& S0 = p.st[0];
         const int plane = S0.in_slots * 16;
         const int lo_off = nch0 * plane;
@@ -355,22 +426,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
         int dsto[TC_ZITEMS];
 #pragma unroll
         for (int it = 0; it < TC_ZITEMS; ++it) {
-          const int idx = tid + it * TC_WTHREADS;
+          const int idx = gtid + it * TC_GTHREADS;
           dsto[it] = -1;
           if (idx < n_zitems) {
-            const int ch = idx / p.WIN;
+            const int ch = fast_div(idx, p.WIN, p.mg_win);
             const int sl = idx - ch * p.WIN;
             dsto[it] = ch * plane + sl * 16;
-            const SlotInfo si = decode_slot(p, (t0 + kz) * TC_TILE + sl);
+            const SlotInfo si = decode_slot(p, (t0 + kz) * TC_TILE + sl, HW);
             if (si.valid) {
-              const size_t g = ((size_t)si.n * p.C + ch * 8) * p.HW + si.gp;
+              const size_t g = ((size_t)si.n * p.C + ch * 8) * HW + si.gp;
 #pragma unroll
-              for (int e = 0; e < 8; ++e) v[it][e] = __ldg(p.z + g + (size_t)e * p.HW);
+              for (int e = 0; e < 8; ++e) v[it][e] = __ldg(p.z + g + (size_t)e * HW);
               if (MODE == IAF_MODE_LAYER) {  // z0 = mean + exp(logsd) * eps   (tf_train.py:57, distributions.py:20)
 #pragma unroll
                 for (int e = 0; e < 8; ++e)
-                  v[it][e] = fmaf(__expf(__ldg(p.post_logsd + g + (size_t)e * p.HW)), v[it][e],
-                                  __ldg(p.post_mean + g + (size_t)e * p.HW));
+                  v[it][e] = fmaf(fast_exp(__ldg(p.post_logsd + g + (size_t)e * HW)), v[it][e],
+                                  __ldg(p.post_mean + g + (size_t)e * HW));
               }
             } else {
 #pragma unroll
@@ -378,7 +449,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
             }
           }
         }
+        if (gwarp == 0 && lane == 0) TL(1 + grp, 30, kz);
         if (kz >= 1) mbar_wait(&bars[BAR_ZEMPTY], (uint32_t)((kz - 1) & 1));  // M0(kz-1) has drained the window
+        if (gwarp == 0 && lane == 0) TL(1 + grp, 31, kz);
 #pragma unroll
         for (int it = 0; it < TC_ZITEMS; ++it) {
           if (dsto[it] >= 0) {
@@ -389,19 +462,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[BAR_ZFULL]);
+        if (gwarp == 0 && lane == 0) TL(1 + grp, 32, kz);
       }
 
       // ------------------------------ E_j(s - 2j) ---------------------------------------------
       for (int j = 0; j < nst; ++j) {
         const int k = s - 2 * j;
-        if (k < 0 || k >= nt + (nst - 1 - j)) continue;
+        if (k < 0 || k >= nt + (nst - 1 - j) || (TC_NGROUPS == 2 && (k & 1) != grp)) continue;
         const IafTcStage& St = p.st[j];
         const bool last = (j == nst - 1);
+        if (gwarp == 0 && lane == 0) TL(1 + grp, 10 + j, k);
         const int b = St.dbl ? (k & 1) : 0;
         const int use = St.dbl ? (k >> 1) : k;
         const int u = t0 + k;
         const int sl = q * 32 + lane;
-        const SlotInfo si = decode_slot(p, u * TC_TILE + sl);
+        const SlotInfo si = decode_slot(p, u * TC_TILE + sl, HW);
         const bool bx0 = (si.x == 0), bxW = (si.x == p.W - 1), byH = (si.y == p.H - 1);
         const float* tb = reinterpret_cast<const float*>(smem + St.sm_bias);
         const uint32_t t_acc = t_lane + (uint32_t)(St.tmem_col + b * St.N);
@@ -414,13 +489,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
           uint8_t* obase = smem + Nx.sm_in + ((k & 1) * TC_TILE + sl) * 16;
           const bool mirror = ((k & 1) == 0) && (sl < p.MIR);
           bool waited = false;
-          for (int g = cg; g < ngroups; g += 4) {
+          for (int g = cg; g < ngroups; g += CGS) {
             const int c0 = g * 16;
             float cx[16];
             if (j == 0 && si.valid) {  // += context   (ar.py:402 / layers.py:163)
-              const float* cp = p.ctx + ((size_t)si.n * St.N + c0) * p.HW + si.gp;
+              const float* cp = p.ctx + ((size_t)si.n * St.N + c0) * HW + si.gp;
 #pragma unroll
-              for (int e = 0; e < 16; ++e) cx[e] = __ldg(cp + (size_t)e * p.HW);
+              for (int e = 0; e < 16; ++e) cx[e] = __ldg(cp + (size_t)e * HW);
             } else {
 #pragma unroll
               for (int e = 0; e < 16; ++e) cx[e] = 0.f;
@@ -429,7 +504,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
               mbar_wait(&bars[BAR_ACC_FULL + 2 * j + b], (uint32_t)(use & 1));
               tc_fence_after();
               // ring slot k&1 was last read by M_{j+1}(k-2)
+              if (gwarp == 0 && lane == 0) TL(1 + grp, 40 + j, k);
               if (k >= 2) mbar_wait(&bars[BAR_H_EMPTY + 2 * j + (k & 1)], (uint32_t)(((k >> 1) - 1) & 1));
+              if (gwarp == 0 && lane == 0) TL(1 + grp, 50 + j, k);
               waited = true;
             }
             uint32_t r[16];
@@ -464,6 +541,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
             mbar_arrive(&bars[BAR_ACC_EMPTY + 2 * j + b]);
             mbar_arrive(&bars[BAR_H_FULL + 2 * j + (k & 1)]);
           }
+          if (gwarp == 0 && lane == 0) TL(1 + grp, 20 + j, k);
         } else {
           // ---------------- heads: columns in groups of 16 = (m x 8, s x 8) of 8 channels --------------
           constexpr int NRED = (MODE == IAF_MODE_LAYER) ? 8 : 1;
@@ -471,24 +549,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
 #pragma unroll
           for (int i = 0; i < NRED; ++i) red[i] = 0.f;
           const int tile_s0 = u * TC_TILE;
-          const int n_first = (int)((unsigned)tile_s0 / (unsigned)p.SPS);
-          const int n_last = min(p.B - 1, (int)((unsigned)(tile_s0 + TC_TILE - 1) / (unsigned)p.SPS));
+          const int n_first = fast_div(tile_s0, p.SPS, p.mg_sps);
+          const int n_last = min(p.B - 1, fast_div(tile_s0 + TC_TILE - 1, p.SPS, p.mg_sps));
           const int ns = (tile_s0 < p.S) ? (n_last - n_first + 1) : 0;
+          const int pb = k & 1;  // partial-sum buffer
           bool waited = false;
-          for (int g = cg; g < ngroups; g += 4) {
+          for (int g = cg; g < ngroups; g += CGS) {
             const int c0 = g * 16;
             const int ch0 = g * 8;
             float zv[8];
             size_t gi = 0;
             if (si.valid) {
-              gi = ((size_t)si.n * p.C + ch0) * p.HW + si.gp;
+              gi = ((size_t)si.n * p.C + ch0) * HW + si.gp;
 #pragma unroll
-              for (int e = 0; e < 8; ++e) zv[e] = __ldg(p.z + gi + (size_t)e * p.HW);
+              for (int e = 0; e < 8; ++e) zv[e] = __ldg(p.z + gi + (size_t)e * HW);
             }
             if (!waited) {
               mbar_wait(&bars[BAR_ACC_FULL + 2 * j + b], (uint32_t)(use & 1));
               tc_fence_after();
               waited = true;
+              if (gwarp == 0 && lane == 0) TL(1 + grp, 50 + j, k);
             }
             uint32_t r[16];
             tmem_ld16(t_acc + (uint32_t)c0, r);
@@ -509,15 +589,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
                   if (byH || bxW) { m += tb[4 * St.N + c0 + e]; sv += tb[4 * St.N + c0 + 8 + e]; }
                 }
                 const float arw_mean = p.scale * m, arw_logsd = p.scale * sv;  // models.py:282-285
-                const size_t ge = gi + (size_t)e * p.HW;
+                const size_t ge = gi + (size_t)e * HW;
                 float z0 = zv[e];
                 float eps = 0.f, pls = 0.f;
                 if (MODE == IAF_MODE_LAYER) {
                   eps = z0;
                   pls = __ldg(p.post_logsd + ge);
-                  z0 = fmaf(__expf(pls), eps, __ldg(p.post_mean + ge));
+                  z0 = fmaf(fast_exp(pls), eps, __ldg(p.post_mean + ge));
                 }
-                const float zn = (z0 - arw_mean) * __expf(-arw_logsd);
+                const float zn = (z0 - arw_mean) * fast_exp(-arw_logsd);
                 p.z_out[ge] = zn;
                 if (MODE == IAF_MODE_STEP) {
                   if (p.elem) p.elem[ge] = arw_logsd;
@@ -527,7 +607,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
                   const float logqs = -0.9189385332046727f - pls - 0.5f * eps * eps + arw_logsd;
                   const float pl = __ldg(p.prior_logsd + ge);
                   const float d = zn - __ldg(p.prior_mean + ge);
-                  const float logps = -0.9189385332046727f - pl - 0.5f * d * d * __expf(-2.0f * pl);
+                  const float logps = -0.9189385332046727f - pl - 0.5f * d * d * fast_exp(-2.0f * pl);
                   const float kl = logqs - logps;
                   if (p.elem) p.elem[ge] = kl;
                   red[e] = kl;
@@ -542,7 +622,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
                   float x = (si.valid && si.n == n_first + nl_) ? red[e] : 0.f;
 #pragma unroll
                   for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-                  if (lane == 0) s_part[(q * p.MAXS + nl_) * p.C + ch0 + e] = x;
+                  if (lane == 0) s_part[((pb * 4 + q) * p.MAXS + nl_) * p.C + ch0 + e] = x;
                 }
               }
             }
@@ -551,52 +631,60 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars[BAR_ACC_EMPTY + 2 * j + b]);
+          if (gwarp == 0 && lane == 0) TL(1 + grp, 20 + j, k);
 
           // ---------------- deterministic per-sample reductions ----------------
+          // every worker warp deposits fixed-order partial sums for this tile in smem (double-buffered by
+          // tile parity), arrives on an mbarrier and moves on; worker warp 0 alone folds them into the
+          // per-tile partials in global memory and, for samples whose last tile this is, into the outputs.
           if (p.persample_out || p.bc_out) {
-            if (MODE == IAF_MODE_STEP) {
+            constexpr bool LAY = (MODE == IAF_MODE_LAYER);
+            if (!LAY) {
               for (int nl_ = 0; nl_ < ns; ++nl_) {
                 float x = (si.valid && si.n == n_first + nl_) ? red[0] : 0.f;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-                if (lane == 0) s_part[warp * p.MAXS + nl_] = x;
+                if (lane == 0) s_part[(pb * TC_GWARPS + gwarp) * p.MAXS + nl_] = x;
               }
             }
-            worker_bar_sync();
-            constexpr bool LAY = (MODE == IAF_MODE_LAYER);
-            const int cred = LAY ? p.C : 1;
-            // tile partials -> global, fixed summation order
-            for (int i = tid; i < ns * cred; i += TC_WTHREADS) {
-              float tot = 0.f;
-              if (LAY) {
-                const int nl_ = i / p.C, c = i - nl_ * p.C;
-                for (int qq = 0; qq < 4; ++qq) tot += s_part[(qq * p.MAXS + nl_) * p.C + c];
-              } else {
-                for (int w = 0; w < TC_WORKERS; ++w) tot += s_part[w * p.MAXS + i];
-              }
-              p.tilepart[((size_t)u * p.MAXS) * cred + i] = tot;
-            }
-            __threadfence();
-            worker_bar_sync();
-            if (tid < ns) {
-              const int n = n_first + tid;
-              const int a = n * p.SPS, bb = a + p.SPS - 1;
-              const int ta = a / TC_TILE, tbk = bb / TC_TILE;
-              const unsigned expected = (unsigned)(tbk - ta + 1);
-              if (atomicAdd(p.counter + n, 1u) == expected - 1u) {
-                __threadfence();
-                p.counter[n] = 0u;  // ready for the next launch
-                float cost = 0.f;
-                for (int c = 0; c < cred; ++c) {
-                  float tot = 0.f;
-                  for (int tt = ta; tt <= tbk; ++tt) {
-                    const int nf = (int)((unsigned)(tt * TC_TILE) / (unsigned)p.SPS);
-                    tot += __ldcg(p.tilepart + ((size_t)tt * p.MAXS + (n - nf)) * cred + c);
-                  }
-                  if (LAY && p.bc_out) p.bc_out[(size_t)n * p.C + c] = tot;
-                  cost += tot;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[BAR_PART + pb]);
+            if (gwarp == 0) {
+              mbar_wait(&bars[BAR_PART + pb], (uint32_t)((k >> 1) & 1));
+              const int cred = LAY ? p.C : 1;
+              for (int i = lane; i < ns * cred; i += 32) {
+                float tot = 0.f;
+                if (LAY) {
+                  const int nl_ = i / p.C, c = i - nl_ * p.C;
+                  for (int qq = 0; qq < 4; ++qq) tot += s_part[((pb * 4 + qq) * p.MAXS + nl_) * p.C + c];
+                } else {
+                  for (int w = 0; w < TC_GWARPS; ++w) tot += s_part[(pb * TC_GWARPS + w) * p.MAXS + i];
                 }
-                if (p.persample_out) p.persample_out[n] = LAY ? cost : -cost;  // logdet = -sum(arw_logsd)
+                p.tilepart[((size_t)u * p.MAXS) * cred + i] = tot;
+                __threadfence();
+              }
+              __syncwarp();
+              for (int i = lane; i < ns; i += 32) {
+                const int n = n_first + i;
+                const int a = n * p.SPS, bb = a + p.SPS - 1;
+                const int ta = a / TC_TILE, tbk = bb / TC_TILE;
+                const unsigned expected = (unsigned)(tbk - ta + 1);
+                __threadfence();
+                if (atomicAdd(p.counter + n, 1u) == expected - 1u) {
+                  __threadfence();
+                  p.counter[n] = 0u;  // ready for the next launch
+                  float cost = 0.f;
+                  for (int c = 0; c < cred; ++c) {
+                    float tot = 0.f;
+                    for (int tt = ta; tt <= tbk; ++tt) {
+                      const int nf = fast_div(tt * TC_TILE, p.SPS, p.mg_sps);
+                      tot += __ldcg(p.tilepart + ((size_t)tt * p.MAXS + (n - nf)) * cred + c);
+                    }
+                    if (LAY && p.bc_out) p.bc_out[(size_t)n * p.C + c] = tot;
+                    cost += tot;
+                  }
+                  if (p.persample_out) p.persample_out[n] = LAY ? cost : -cost;  // logdet = -sum(arw_logsd)
+                }
               }
             }
           }
@@ -607,6 +695,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
 
   tc_fence_before();
   __syncthreads();
+  TL_FLUSH
   if (warp == TC_CTRL_WARP) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
@@ -712,13 +801,18 @@ struct IafTcPlan {
 };
 
 typedef void (*TcKernel)(const IafTcParams);
-static TcKernel tc_kernel_for(bool padw, int mode, bool elu) {
+template <int THW>
+static TcKernel tc_kernel_pick(bool padw, int mode, bool elu) {
   if (mode == IAF_MODE_STEP) {
-    if (padw) return elu ? iaf_tc_kernel<true, IAF_MODE_STEP, IAF_NL_ELU> : iaf_tc_kernel<true, IAF_MODE_STEP, -1>;
-    return elu ? iaf_tc_kernel<false, IAF_MODE_STEP, IAF_NL_ELU> : iaf_tc_kernel<false, IAF_MODE_STEP, -1>;
+    if (padw) return elu ? iaf_tc_kernel<true, IAF_MODE_STEP, IAF_NL_ELU, THW> : iaf_tc_kernel<true, IAF_MODE_STEP, -1, THW>;
+    return elu ? iaf_tc_kernel<false, IAF_MODE_STEP, IAF_NL_ELU, THW> : iaf_tc_kernel<false, IAF_MODE_STEP, -1, THW>;
   }
-  if (padw) return elu ? iaf_tc_kernel<true, IAF_MODE_LAYER, IAF_NL_ELU> : iaf_tc_kernel<true, IAF_MODE_LAYER, -1>;
-  return elu ? iaf_tc_kernel<false, IAF_MODE_LAYER, IAF_NL_ELU> : iaf_tc_kernel<false, IAF_MODE_LAYER, -1>;
+  if (padw) return elu ? iaf_tc_kernel<true, IAF_MODE_LAYER, IAF_NL_ELU, THW> : iaf_tc_kernel<true, IAF_MODE_LAYER, -1, THW>;
+  return elu ? iaf_tc_kernel<false, IAF_MODE_LAYER, IAF_NL_ELU, THW> : iaf_tc_kernel<false, IAF_MODE_LAYER, -1, THW>;
+}
+// 16x16 planes (every BASELINE config's first level) get compile-time channel strides
+static TcKernel tc_kernel_for(bool padw, int mode, bool elu, int hw) {
+  return hw == 256 ? tc_kernel_pick<256>(padw, mode, elu) : tc_kernel_pick<0>(padw, mode, elu);
 }
 
 static int tc_round_up(int a, int b) { return (a + b - 1) / b * b; }
@@ -738,7 +832,7 @@ static bool tc_layout(const iaf_desc_t* d, IafTcPlan* pl) {
   q->n_stages = nst;
   q->MIR = MIR; q->WIN = TC_TILE + MIR; q->RING = 2 * TC_TILE + MIR;
   q->MAXS = (TC_TILE - 1) / SPS + 2;
-  if ((d->n_z / 8) * q->WIN > TC_ZITEMS * TC_WTHREADS) return false;
+  if ((d->n_z / 8) * q->WIN > TC_ZITEMS * TC_GTHREADS) return false;
   int off = 0, prev = d->n_z;
   for (int j = 0; j < nst; ++j) {
     q->cin[j] = prev;
@@ -760,8 +854,8 @@ static bool tc_layout(const iaf_desc_t* d, IafTcPlan* pl) {
   }
   off = tc_round_up(off, 16);
   q->sm_part = off;
-  const int part_step = TC_WORKERS * q->MAXS * 4;
-  const int part_layer = 4 * q->MAXS * d->n_z * 4;
+  const int part_step = 2 * TC_GWARPS * q->MAXS * 4;
+  const int part_layer = 2 * 4 * q->MAXS * d->n_z * 4;
   q->layer_ok = (off + std::max(part_step, part_layer)) <= TC_SMEM_LIMIT;
   off += q->layer_ok ? std::max(part_step, part_layer) : part_step;
   // TMEM: double-buffer as many accumulators as fit in 512 columns, the heads first
@@ -802,7 +896,7 @@ int iaf_tc_plan_create(IafTcPlan** out, const iaf_desc_t* d) {
     }
   }
   for (int a = 0; a < 8; ++a) {
-    TcKernel k = tc_kernel_for(a & 1, (a & 2) ? IAF_MODE_LAYER : IAF_MODE_STEP, a & 4);
+    TcKernel k = tc_kernel_for(a & 1, (a & 2) ? IAF_MODE_LAYER : IAF_MODE_STEP, a & 4, d->H * d->W);
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem) != cudaSuccess) {
       iaf_tc_plan_destroy(pl);
       return IAF_ERR_CUDA;
@@ -857,6 +951,25 @@ int iaf_tc_pack(IafTcPlan* pl, const float* const* w, const float* const* scale,
   return cudaGetLastError() == cudaSuccess ? IAF_OK : IAF_ERR_CUDA;
 }
 
+#ifdef IAF_TC_TIMELINE
+extern "C" void iaf_tc_timeline_dump(void) {
+  cudaDeviceSynchronize();
+  static long long h[3][TL_MAX][3];
+  int n[3];
+  cudaMemcpyFromSymbol(h, g_tl, sizeof(h));
+  cudaMemcpyFromSymbol(n, g_tl_n, sizeof(n));
+  long long t0 = -1;
+  for (int r = 0; r < 3; ++r)
+    for (int i = 0; i < n[r] && i < TL_MAX; ++i)
+      if (t0 < 0 || h[r][i][2] < t0) t0 = h[r][i][2];
+  for (int r = 0; r < 3; ++r)
+    for (int i = 0; i < n[r] && i < TL_MAX; ++i)
+      printf("TL role=%d tag=%lld k=%lld t=%lld\n", r, h[r][i][0], h[r][i][1], h[r][i][2] - t0);
+  int z[3] = {0, 0, 0};
+  cudaMemcpyToSymbol(g_tl_n, z, sizeof(z));
+}
+#endif
+
 bool iaf_tc_mode_supported(const IafTcPlan* pl, int mode) { return mode == IAF_MODE_STEP || (mode == IAF_MODE_LAYER && pl->layer_ok); }
 
 int iaf_tc_run(IafTcPlan* pl, const IafTcArgs* a, cudaStream_t stream, int* n_launches) {
@@ -901,8 +1014,11 @@ int iaf_tc_run(IafTcPlan* pl, const IafTcArgs* a, cudaStream_t stream, int* n_la
   p.flip = d.variant == IAF_VARIANT_THEANO ? 1 : 0;
   p.nl = d.nl; p.scale = 0.1f;
   p.tmem_cols = pl->tmem_cols;
+  p.mg_sps = (unsigned)((1ULL << 32) / (unsigned)SPS) + 1u;
+  p.mg_wp = (unsigned)((1ULL << 32) / (unsigned)p.Wp) + 1u;
+  p.mg_win = (unsigned)((1ULL << 32) / (unsigned)p.WIN) + 1u;
   const int grid = std::min(pl->num_sms, NT);
-  TcKernel k = tc_kernel_for(d.variant == IAF_VARIANT_THEANO, a->mode, d.nl == IAF_NL_ELU);
+  TcKernel k = tc_kernel_for(d.variant == IAF_VARIANT_THEANO, a->mode, d.nl == IAF_NL_ELU, d.H * d.W);
   k<<<grid, TC_THREADS, pl->smem, stream>>>(p);
   if (n_launches) *n_launches = 1;
   return cudaGetLastError() == cudaSuccess ? IAF_OK : IAF_ERR_CUDA;
