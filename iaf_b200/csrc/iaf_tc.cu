@@ -699,6 +699,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
   if (warp == TC_CTRL_WARP) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
+#include "iaf_tc_gemm.cuh"
+
 // ------------------------------------------------------------------------------------------
 // weight preparation for this path: same math as iaf_pack.cu, bf16 hi/lo split, written as
 // the UMMA B-operand image [K/8][N][8] (K index = tap*Cin + ci, K-major, no swizzle).
@@ -793,6 +795,13 @@ struct IafTcPlan {
   int sm_bias[IAF_MAX_STAGES], tmem_col[IAF_MAX_STAGES], dbl[IAF_MAX_STAGES];
   int MIR, WIN, RING, MAXS, sm_part, tmem_cols;
   bool layer_ok;             // the per-(sample,channel) scratch of the fused-layer mode fits
+  // layer-at-a-time mode (hidden widths that do not fit the fused kernel's on-chip rings)
+  bool layered;
+  int ly_NB[IAF_MAX_STAGES], ly_sm_a[IAF_MAX_STAGES], ly_sm_b[IAF_MAX_STAGES], ly_sm_bias[IAF_MAX_STAGES],
+      ly_sm_part[IAF_MAX_STAGES], ly_tmem[IAF_MAX_STAGES];
+  size_t ly_smem[IAF_MAX_STAGES];
+  __nv_bfloat16* img[2][2];  // ping-pong operand images: [which][hi|lo]
+  int img_S_pad;
   size_t smem;
   unsigned* counter;
   float* tilepart;
@@ -813,6 +822,20 @@ static TcKernel tc_kernel_pick(bool padw, int mode, bool elu) {
 // 16x16 planes (every BASELINE config's first level) get compile-time channel strides
 static TcKernel tc_kernel_for(bool padw, int mode, bool elu, int hw) {
   return hw == 256 ? tc_kernel_pick<256>(padw, mode, elu) : tc_kernel_pick<0>(padw, mode, elu);
+}
+
+typedef void (*LyKernel)(const IafLyParams);
+template <int THW>
+static LyKernel ly_kernel_pick(bool padw, int mode, bool elu) {
+  if (mode == IAF_MODE_STEP) {
+    if (padw) return elu ? iaf_ly_kernel<true, IAF_MODE_STEP, IAF_NL_ELU, THW> : iaf_ly_kernel<true, IAF_MODE_STEP, -1, THW>;
+    return elu ? iaf_ly_kernel<false, IAF_MODE_STEP, IAF_NL_ELU, THW> : iaf_ly_kernel<false, IAF_MODE_STEP, -1, THW>;
+  }
+  if (padw) return elu ? iaf_ly_kernel<true, IAF_MODE_LAYER, IAF_NL_ELU, THW> : iaf_ly_kernel<true, IAF_MODE_LAYER, -1, THW>;
+  return elu ? iaf_ly_kernel<false, IAF_MODE_LAYER, IAF_NL_ELU, THW> : iaf_ly_kernel<false, IAF_MODE_LAYER, -1, THW>;
+}
+static LyKernel ly_kernel_for(bool padw, int mode, bool elu, int hw) {
+  return hw == 256 ? ly_kernel_pick<256>(padw, mode, elu) : ly_kernel_pick<0>(padw, mode, elu);
 }
 
 static int tc_round_up(int a, int b) { return (a + b - 1) / b * b; }
@@ -873,14 +896,63 @@ static bool tc_layout(const iaf_desc_t* d, IafTcPlan* pl) {
   return off <= TC_SMEM_LIMIT;
 }
 
-bool iaf_tc_supported(const iaf_desc_t* d) { return tc_layout(d, nullptr); }
+// layer-at-a-time layout: per stage an A window, an NB-deep weight ring, the bias table and the partial scratch
+static bool ly_layout(const iaf_desc_t* d, IafTcPlan* pl) {
+  if (d->n_hidden < 1 || d->n_heads != 2 || d->head[0] != d->n_z || d->head[1] != d->n_z) return false;
+  if (d->n_z % 16 != 0 || 2 * d->n_z > 256) return false;
+  for (int i = 0; i < d->n_hidden; ++i)
+    if (d->hidden[i] % 16 != 0 || d->hidden[i] > 256) return false;
+  const int nst = d->n_hidden + 1;
+  const int Wp = d->W + 1;
+  const int SPS = (d->H + 1) * Wp;
+  const int MIR = tc_round_up(Wp + 1, 8);
+  if (MIR > TC_TILE) return false;
+  IafTcPlan tmp;
+  IafTcPlan* q = pl ? pl : &tmp;
+  q->n_stages = nst;
+  q->MIR = MIR; q->WIN = TC_TILE + MIR; q->RING = 0;
+  q->MAXS = (TC_TILE - 1) / SPS + 2;
+  if ((d->n_z / 8) * q->WIN > TC_ZITEMS * LY_WTHREADS) return false;
+  int prev = d->n_z;
+  q->layer_ok = true;
+  for (int j = 0; j < nst; ++j) {
+    q->cin[j] = prev;
+    q->N[j] = (j < d->n_hidden) ? d->hidden[j] : 2 * d->n_z;
+    q->K[j] = IAF_NTAPS * prev;
+    prev = q->N[j];
+    int off = 0;
+    q->ly_sm_a[j] = off; off += 2 * (q->cin[j] / 8) * q->WIN * 16;
+    q->ly_sm_bias[j] = off; off += 5 * q->N[j] * 4;
+    off = tc_round_up(off, 16);
+    q->ly_sm_part[j] = off;
+    off += std::max(2 * LY_WORKERS * q->MAXS * 4, 2 * 4 * q->MAXS * d->n_z * 4);
+    off = tc_round_up(off, 128);
+    q->ly_sm_b[j] = off;
+    const int slot = 2 * LY_KC * 2 * q->N[j] * 16;  // hi + lo halves of one ring slot
+    int nb = (TC_SMEM_LIMIT - off) / slot;
+    if (nb < 2) return false;
+    q->ly_NB[j] = std::min(nb, LY_MAX_NB);
+    q->ly_smem[j] = (size_t)off + (size_t)q->ly_NB[j] * slot;
+    if (2 * q->N[j] > 512) return false;
+    int tc = 32;
+    while (tc < 2 * q->N[j]) tc *= 2;
+    q->ly_tmem[j] = tc;
+  }
+  return true;
+}
+
+bool iaf_tc_supported(const iaf_desc_t* d) { return tc_layout(d, nullptr) || ly_layout(d, nullptr); }
 
 int iaf_tc_plan_create(IafTcPlan** out, const iaf_desc_t* d) {
   IafTcPlan* pl = new (std::nothrow) IafTcPlan();
   if (!pl) return IAF_ERR_BAD_ARG;
   memset(pl, 0, sizeof(*pl));
   pl->d = *d;
-  if (!tc_layout(d, pl)) { delete pl; return IAF_ERR_UNSUPPORTED; }
+  pl->layered = false;
+  if (!tc_layout(d, pl)) {
+    if (!ly_layout(d, pl)) { delete pl; return IAF_ERR_UNSUPPORTED; }
+    pl->layered = true;
+  }
   int dev = 0;
   cudaDeviceProp prop;
   if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { delete pl; return IAF_ERR_CUDA; }
@@ -895,9 +967,17 @@ int iaf_tc_plan_create(IafTcPlan** out, const iaf_desc_t* d) {
       return IAF_ERR_CUDA;
     }
   }
+  size_t ly_max = 0;
+  for (int j = 0; j < pl->n_stages; ++j) ly_max = std::max(ly_max, pl->ly_smem[j]);
   for (int a = 0; a < 8; ++a) {
-    TcKernel k = tc_kernel_for(a & 1, (a & 2) ? IAF_MODE_LAYER : IAF_MODE_STEP, a & 4, d->H * d->W);
-    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem) != cudaSuccess) {
+    cudaError_t e;
+    if (pl->layered)
+      e = cudaFuncSetAttribute(ly_kernel_for(a & 1, (a & 2) ? IAF_MODE_LAYER : IAF_MODE_STEP, a & 4, d->H * d->W),
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ly_max);
+    else
+      e = cudaFuncSetAttribute(tc_kernel_for(a & 1, (a & 2) ? IAF_MODE_LAYER : IAF_MODE_STEP, a & 4, d->H * d->W),
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem);
+    if (e != cudaSuccess) {
       iaf_tc_plan_destroy(pl);
       return IAF_ERR_CUDA;
     }
@@ -916,6 +996,9 @@ void iaf_tc_plan_destroy(IafTcPlan* pl) {
   }
   if (pl->counter) cudaFree(pl->counter);
   if (pl->tilepart) cudaFree(pl->tilepart);
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b)
+      if (pl->img[a][b]) cudaFree(pl->img[a][b]);
   delete pl;
 }
 int iaf_tc_pack(IafTcPlan* pl, const float* const* w, const float* const* scale, const float* const* bias,
@@ -971,6 +1054,7 @@ extern "C" void iaf_tc_timeline_dump(void) {
 #endif
 
 bool iaf_tc_mode_supported(const IafTcPlan* pl, int mode) { return mode == IAF_MODE_STEP || (mode == IAF_MODE_LAYER && pl->layer_ok); }
+bool iaf_tc_is_layered(const IafTcPlan* pl) { return pl->layered; }
 
 int iaf_tc_run(IafTcPlan* pl, const IafTcArgs* a, cudaStream_t stream, int* n_launches) {
   const iaf_desc_t& d = pl->d;
@@ -983,6 +1067,19 @@ int iaf_tc_run(IafTcPlan* pl, const IafTcArgs* a, cudaStream_t stream, int* n_la
     if (pl->counter) cudaFree(pl->counter);
     if (pl->tilepart) cudaFree(pl->tilepart);
     pl->counter = nullptr; pl->tilepart = nullptr; pl->scratch_B = 0;
+    if (pl->layered) {
+      int maxc = 0;
+      for (int j = 0; j + 1 < pl->n_stages; ++j) maxc = std::max(maxc, pl->N[j]);
+      pl->img_S_pad = (NT + 1) * TC_TILE;  // one zero tile past the end: windows of the last tile read into it
+      const size_t bytes = (size_t)(maxc / 8) * pl->img_S_pad * 16;
+      for (int a2 = 0; a2 < 2; ++a2)
+        for (int b2 = 0; b2 < 2; ++b2) {
+          if (pl->img[a2][b2]) cudaFree(pl->img[a2][b2]);
+          pl->img[a2][b2] = nullptr;
+          if (cudaMalloc(&pl->img[a2][b2], bytes) != cudaSuccess) return IAF_ERR_CUDA;
+          if (cudaMemset(pl->img[a2][b2], 0, bytes) != cudaSuccess) return IAF_ERR_CUDA;
+        }
+    }
     if (cudaMalloc(&pl->counter, sizeof(unsigned) * (size_t)B) != cudaSuccess) return IAF_ERR_CUDA;
     if (cudaMemset(pl->counter, 0, sizeof(unsigned) * (size_t)B) != cudaSuccess) return IAF_ERR_CUDA;
     if (cudaMalloc(&pl->tilepart, sizeof(float) * (size_t)NT * pl->MAXS * d.n_z) != cudaSuccess) return IAF_ERR_CUDA;
@@ -1018,6 +1115,33 @@ int iaf_tc_run(IafTcPlan* pl, const IafTcArgs* a, cudaStream_t stream, int* n_la
   p.mg_wp = (unsigned)((1ULL << 32) / (unsigned)p.Wp) + 1u;
   p.mg_win = (unsigned)((1ULL << 32) / (unsigned)p.WIN) + 1u;
   const int grid = std::min(pl->num_sms, NT);
+  if (pl->layered) {
+    LyKernel lk = ly_kernel_for(d.variant == IAF_VARIANT_THEANO, a->mode, d.nl == IAF_NL_ELU, d.H * d.W);
+    for (int j = 0; j < pl->n_stages; ++j) {
+      IafLyParams q;
+      memset(&q, 0, sizeof(q));
+      q.t = p;
+      q.t.st[0] = p.st[j];
+      q.t.n_stages = 1;
+      q.t.tmem_cols = pl->ly_tmem[j];
+      q.t.sm_part = pl->ly_sm_part[j];
+      q.a_hi = j ? pl->img[(j - 1) & 1][0] : nullptr;
+      q.a_lo = j ? pl->img[(j - 1) & 1][1] : nullptr;
+      q.o_hi = pl->img[j & 1][0];
+      q.o_lo = pl->img[j & 1][1];
+      q.S_pad = pl->img_S_pad;
+      q.in_mode = j ? 1 : 0;
+      q.first = j == 0;
+      q.is_heads = j == pl->n_stages - 1;
+      q.NB = pl->ly_NB[j];
+      q.sm_a = pl->ly_sm_a[j]; q.sm_b = pl->ly_sm_b[j]; q.sm_bias = pl->ly_sm_bias[j]; q.sm_part = pl->ly_sm_part[j];
+      q.b_chunk_bytes = LY_KC * 2 * pl->N[j] * 16;
+      q.n_bchunks = (pl->K[j] / 16) / LY_KC;
+      lk<<<grid, LY_THREADS, pl->ly_smem[j], stream>>>(q);
+    }
+    if (n_launches) *n_launches = pl->n_stages;
+    return cudaGetLastError() == cudaSuccess ? IAF_OK : IAF_ERR_CUDA;
+  }
   TcKernel k = tc_kernel_for(d.variant == IAF_VARIANT_THEANO, a->mode, d.nl == IAF_NL_ELU, d.H * d.W);
   k<<<grid, TC_THREADS, pl->smem, stream>>>(p);
   if (n_launches) *n_launches = 1;

@@ -1,0 +1,417 @@
+// Layer-at-a-time tcgen05 kernel for stacks whose hidden width does not fit the fused kernel's
+// on-chip rings (hidden = 160: BASELINE configs C2b/C3/C4/C5).  Included by iaf_tc.cu.
+//
+// One launch per conv stage.  Same slot-stream / implicit-GEMM formulation and bf16 hi/lo operand
+// split as iaf_tc_kernel, but
+//   * the stage's input operand comes from HBM/L2: either fp32 z (stage 0, split on the fly by the
+//     worker warps) or the previous stage's output, stored as pre-split bf16 "operand images"
+//     [channel chunk][slot][8] (hi and lo) so that a tile's A window is 2*Cin/8 contiguous runs that a
+//     producer warp fetches with 1-D TMA bulk copies;
+//   * the weights are NOT resident: a producer warp streams them in chunks of KC K-steps through an
+//     NB-deep shared-memory ring (cp.async.bulk + expect_tx; the MMA warp releases a ring slot with
+//     tcgen05.commit), every CTA re-reading them from L2 once per tile;
+//   * hidden stages write their output operand image back to global memory (16-byte coalesced stores),
+//     the heads stage applies the affine update exactly like the fused kernel.
+// Accumulators are double-buffered in TMEM, so the epilogue of tile i overlaps the loads and MMAs of
+// tile i+1.
+#pragma once
+
+#define LY_WORKERS 16
+#define LY_WTHREADS (LY_WORKERS * 32)
+#define LY_MMA_WARP LY_WORKERS
+#define LY_TMA_WARP (LY_WORKERS + 1)
+#define LY_THREADS (LY_WTHREADS + 64)
+#define LY_KC 5        // K-steps (of 16) per weight chunk
+#define LY_MAX_NB 6
+
+enum { LB_AFULL = 0, LB_AEMPTY = 1, LB_ACC_FULL = 2, LB_ACC_EMPTY = 4, LB_BFULL = 6, LB_BEMPTY = 6 + LY_MAX_NB,
+       LB_PART = 6 + 2 * LY_MAX_NB, LB_COUNT = 8 + 2 * LY_MAX_NB };
+
+struct IafLyParams {
+  IafTcParams t;               // geometry, pointers, slot decoding (t.st[0] describes THIS stage)
+  const __nv_bfloat16* a_hi;   // input operand image (in_mode 1)
+  const __nv_bfloat16* a_lo;
+  __nv_bfloat16* o_hi;         // output operand image (hidden stages)
+  __nv_bfloat16* o_lo;
+  int S_pad;                   // slots per chunk plane of the global images
+  int in_mode;                 // 0: fp32 z (first stage), 1: operand image
+  int is_heads;                // 1: last stage
+  int first;                   // 1: first stage (adds the context)
+  int NB;                      // weight ring depth
+  int sm_a, sm_b, sm_bias, sm_part;
+  int b_chunk_bytes;           // bytes of one ring slot half (hi or lo): LY_KC * 2 * N * 16
+  int n_bchunks;               // weight chunks per tile
+};
+
+template <bool PADW, int MODE, int NLT, int THW>
+__global__ void __launch_bounds__(LY_THREADS, 1) iaf_ly_kernel(const __grid_constant__ IafLyParams q) {
+  const IafTcParams& p = q.t;
+  const int HW = THW ? THW : p.HW;
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bars[LB_COUNT];
+  __shared__ uint32_t s_tmem;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const IafTcStage& St = p.st[0];
+  const int nchunk = St.cin >> 3;
+  const int a_plane = p.WIN * 16;          // bytes per chunk plane of the A window
+  const int a_lo_off = nchunk * a_plane;
+  const int n_my = (p.NT - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // tiles of this CTA
+  const int acc_cols = St.N;
+
+  if (warp == LY_MMA_WARP) {
+    tmem_alloc(&s_tmem, (uint32_t)p.tmem_cols);
+    if (lane == 0) {
+      mbar_init(&bars[LB_AFULL], q.in_mode ? 1 : LY_WORKERS);
+      mbar_init(&bars[LB_AEMPTY], 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&bars[LB_ACC_FULL + i], 1);
+        mbar_init(&bars[LB_ACC_EMPTY + i], LY_WORKERS);
+        mbar_init(&bars[LB_PART + i], LY_WORKERS);
+      }
+      for (int i = 0; i < LY_MAX_NB; ++i) {
+        mbar_init(&bars[LB_BFULL + i], 1);
+        mbar_init(&bars[LB_BEMPTY + i], 1);
+      }
+      fence_barrier_init();
+    }
+  } else if (warp < LY_WORKERS) {
+    float* tb = reinterpret_cast<float*>(smem + q.sm_bias);
+    for (int i = tid; i < 5 * St.N; i += LY_WTHREADS) {
+      float v = 0.f;
+      if (i < St.N) v = __ldg(St.bias + i);
+      else if (PADW) v = __ldg(St.padw + (i - St.N));
+      tb[i] = v;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem;
+
+  if (warp == LY_TMA_WARP) {
+    // ===================== producer: A windows (operand-image input) and the weight ring =====================
+    if (lane == 0) {
+      int gchunk = 0;
+      for (int i = 0; i < n_my; ++i) {
+        const int u = (int)blockIdx.x + i * (int)gridDim.x;
+        if (q.in_mode) {
+          if (i >= 1) mbar_wait(&bars[LB_AEMPTY], (uint32_t)((i - 1) & 1));
+          mbar_expect_tx(&bars[LB_AFULL], (uint32_t)(2 * nchunk * a_plane));
+          for (int c = 0; c < nchunk; ++c) {
+            const size_t go = ((size_t)c * q.S_pad + (size_t)u * TC_TILE) * 8;
+            bulk_g2s(smem + q.sm_a + c * a_plane, q.a_hi + go, (uint32_t)a_plane, &bars[LB_AFULL]);
+            bulk_g2s(smem + q.sm_a + a_lo_off + c * a_plane, q.a_lo + go, (uint32_t)a_plane, &bars[LB_AFULL]);
+          }
+        }
+        for (int c = 0; c < q.n_bchunks; ++c, ++gchunk) {
+          const int stg = gchunk % q.NB;
+          const int use = gchunk / q.NB;
+          if (use >= 1) mbar_wait(&bars[LB_BEMPTY + stg], (uint32_t)((use - 1) & 1));
+          mbar_expect_tx(&bars[LB_BFULL + stg], (uint32_t)(2 * q.b_chunk_bytes));
+          const size_t bo = (size_t)c * q.b_chunk_bytes;
+          uint8_t* dst = smem + q.sm_b + stg * 2 * q.b_chunk_bytes;
+          bulk_g2s(dst, reinterpret_cast<const uint8_t*>(St.whi) + bo, (uint32_t)q.b_chunk_bytes, &bars[LB_BFULL + stg]);
+          bulk_g2s(dst + q.b_chunk_bytes, reinterpret_cast<const uint8_t*>(St.wlo) + bo, (uint32_t)q.b_chunk_bytes,
+                   &bars[LB_BFULL + stg]);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == LY_MMA_WARP) {
+    // ===================== MMA issue (convergent warp, one elected lane) =====================
+    const int ks_per_tap = St.cin >> 4;
+    const uint32_t idesc = umma_idesc(St.N);
+    const uint32_t a_base = smem_u32(smem + q.sm_a);
+    const uint32_t b_plane = (uint32_t)St.N * 16u;
+    int gchunk = 0;
+    for (int i = 0; i < n_my; ++i) {
+      const int b = i & 1, use = i >> 1;
+      mbar_wait(&bars[LB_AFULL], (uint32_t)(i & 1));
+      if (use >= 1) mbar_wait(&bars[LB_ACC_EMPTY + b], (uint32_t)((use - 1) & 1));
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(b * acc_cols);
+      uint32_t acc = 0;
+      int kstep = 0;
+      for (int c = 0; c < q.n_bchunks; ++c, ++gchunk) {
+        const int stg = gchunk % q.NB;
+        mbar_wait(&bars[LB_BFULL + stg], (uint32_t)((gchunk / q.NB) & 1));
+        tc_fence_after();
+        const uint32_t bh0 = smem_u32(smem + q.sm_b + stg * 2 * q.b_chunk_bytes);
+        const uint32_t bl0 = bh0 + (uint32_t)q.b_chunk_bytes;
+        if (elect_one_sync()) {
+#pragma unroll
+          for (int kk = 0; kk < LY_KC; ++kk) {
+            const int ksg = kstep + kk;
+            const int tp = ksg / ks_per_tap, ks = ksg - tp * ks_per_tap;
+            const int shift = (tp < 2) ? tp : p.Wp + tp - 3;  // taps (0,0) (0,+1) (+1,-1) (+1,0) (+1,+1)
+            const uint32_t a_off = (uint32_t)shift * 16u + (uint32_t)(ks * 2) * (uint32_t)a_plane;
+            const uint32_t ah = umma_desc_lo(a_base + a_off, (uint32_t)a_plane);
+            const uint32_t al = umma_desc_lo(a_base + (uint32_t)a_lo_off + a_off, (uint32_t)a_plane);
+            const uint32_t bh = umma_desc_lo(bh0 + (uint32_t)(kk * 2) * b_plane, b_plane);
+            const uint32_t bl = umma_desc_lo(bl0 + (uint32_t)(kk * 2) * b_plane, b_plane);
+            umma_bf16(d_tmem, mk_desc(al), mk_desc(bh), idesc, acc);  // lo * hi
+            acc = 1;
+            umma_bf16(d_tmem, mk_desc(ah), mk_desc(bl), idesc, acc);  // hi * lo
+            umma_bf16(d_tmem, mk_desc(ah), mk_desc(bh), idesc, acc);  // hi * hi
+          }
+          umma_commit(&bars[LB_BEMPTY + stg]);
+        }
+        __syncwarp();
+        kstep += LY_KC;
+      }
+      if (elect_one_sync()) {
+        umma_commit(&bars[LB_ACC_FULL + b]);
+        umma_commit(&bars[LB_AEMPTY]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== workers: (first stage) z -> operand window; epilogues =====================
+    const int qd = warp & 3, cg = warp >> 2;
+    constexpr int CGS = LY_WORKERS / 4;
+    const int sl = qd * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(qd * 32) << 16);
+    const float* tb = reinterpret_cast<const float*>(smem + q.sm_bias);
+    float* s_part = reinterpret_cast<float*>(smem + q.sm_part);
+    const int ngroups = St.N >> 4;
+
+    auto load_window = [&](int i) {  // fp32 z -> bf16 hi/lo A window of this CTA's i-th tile
+      const int u = (int)blockIdx.x + i * (int)gridDim.x;
+      float v[TC_ZITEMS][8];
+      int dsto[TC_ZITEMS];
+#pragma unroll
+      for (int it = 0; it < TC_ZITEMS; ++it) {
+        const int idx = tid + it * LY_WTHREADS;
+        dsto[it] = -1;
+        if (idx < p.WIN * nchunk) {
+          const int ch = fast_div(idx, p.WIN, p.mg_win);
+          const int s_ = idx - ch * p.WIN;
+          dsto[it] = ch * a_plane + s_ * 16;
+          const SlotInfo si = decode_slot(p, u * TC_TILE + s_, HW);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[it][e] = 0.f;
+          if (si.valid) {
+            const size_t g = ((size_t)si.n * p.C + ch * 8) * HW + si.gp;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[it][e] = __ldg(p.z + g + (size_t)e * HW);
+            if (MODE == IAF_MODE_LAYER) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                v[it][e] = fmaf(fast_exp(__ldg(p.post_logsd + g + (size_t)e * HW)), v[it][e],
+                                __ldg(p.post_mean + g + (size_t)e * HW));
+            }
+          }
+        }
+      }
+      if (i >= 1) mbar_wait(&bars[LB_AEMPTY], (uint32_t)((i - 1) & 1));
+#pragma unroll
+      for (int it = 0; it < TC_ZITEMS; ++it) {
+        if (dsto[it] >= 0) {
+          uint8_t* dst = smem + q.sm_a + dsto[it];
+          split_store8(v[it], dst, dst + a_lo_off);
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[LB_AFULL]);
+    };
+
+    if (!q.in_mode && n_my > 0) load_window(0);
+    for (int i = 0; i < n_my; ++i) {
+      if (!q.in_mode && i + 1 < n_my) load_window(i + 1);
+      const int u = (int)blockIdx.x + i * (int)gridDim.x;
+      const int b = i & 1, use = i >> 1;
+      const SlotInfo si = decode_slot(p, u * TC_TILE + sl, HW);
+      const bool bx0 = (si.x == 0), bxW = (si.x == p.W - 1), byH = (si.y == p.H - 1);
+      const uint32_t t_acc = t_lane + (uint32_t)(b * acc_cols);
+
+      if (!q.is_heads) {
+        bool waited = false;
+        for (int g = cg; g < ngroups; g += CGS) {
+          const int c0 = g * 16;
+          float cx[16];
+          if (q.first && si.valid) {  // += context   (ar.py:402 / layers.py:163)
+            const float* cp = p.ctx + ((size_t)si.n * St.N + c0) * HW + si.gp;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) cx[e] = __ldg(cp + (size_t)e * HW);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) cx[e] = 0.f;
+          }
+          if (!waited) {
+            mbar_wait(&bars[LB_ACC_FULL + b], (uint32_t)(use & 1));
+            tc_fence_after();
+            waited = true;
+          }
+          uint32_t r[16];
+          tmem_ld16(t_acc + (uint32_t)c0, r);
+          tmem_ld_wait();
+          float v[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            float a = __uint_as_float(r[e]) + tb[c0 + e] + cx[e];
+            if (PADW) {
+              if (bxW) a += tb[St.N + c0 + e];
+              if (byH || bx0) a += tb[2 * St.N + c0 + e];
+              if (byH) a += tb[3 * St.N + c0 + e];
+              if (byH || bxW) a += tb[4 * St.N + c0 + e];
+            }
+            v[e] = si.valid ? tc_apply_nl<NLT>(a, p.nl) : 0.f;
+          }
+#pragma unroll
+          for (int hch = 0; hch < 2; ++hch) {
+            const size_t go = (((size_t)((c0 >> 3) + hch)) * q.S_pad + (size_t)u * TC_TILE + sl) * 8;
+            split_store8(v + 8 * hch, reinterpret_cast<uint8_t*>(q.o_hi + go), reinterpret_cast<uint8_t*>(q.o_lo + go));
+          }
+        }
+        if (!waited) mbar_wait(&bars[LB_ACC_FULL + b], (uint32_t)(use & 1));
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[LB_ACC_EMPTY + b]);
+      } else {
+        // ---------------- heads: identical arithmetic to iaf_tc_kernel's last stage ----------------
+        constexpr int NRED = (MODE == IAF_MODE_LAYER) ? 8 : 1;
+        float red[NRED];
+#pragma unroll
+        for (int k_ = 0; k_ < NRED; ++k_) red[k_] = 0.f;
+        const int tile_s0 = u * TC_TILE;
+        const int n_first = fast_div(tile_s0, p.SPS, p.mg_sps);
+        const int n_last = min(p.B - 1, fast_div(tile_s0 + TC_TILE - 1, p.SPS, p.mg_sps));
+        const int ns = (tile_s0 < p.S) ? (n_last - n_first + 1) : 0;
+        const int pb = i & 1;
+        bool waited = false;
+        for (int g = cg; g < ngroups; g += CGS) {
+          const int c0 = g * 16;
+          const int ch0 = g * 8;
+          float zv[8];
+          size_t gi = 0;
+          if (si.valid) {
+            gi = ((size_t)si.n * p.C + ch0) * HW + si.gp;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) zv[e] = __ldg(p.z + gi + (size_t)e * HW);
+          }
+          if (!waited) {
+            mbar_wait(&bars[LB_ACC_FULL + b], (uint32_t)(use & 1));
+            tc_fence_after();
+            waited = true;
+          }
+          uint32_t r[16];
+          tmem_ld16(t_acc + (uint32_t)c0, r);
+          tmem_ld_wait();
+          if (MODE == IAF_MODE_LAYER) {
+#pragma unroll
+            for (int k_ = 0; k_ < NRED; ++k_) red[k_] = 0.f;
+          }
+          if (si.valid) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float m = __uint_as_float(r[e]) + tb[c0 + e];
+              float sv = __uint_as_float(r[8 + e]) + tb[c0 + 8 + e];
+              if (PADW) {
+                if (bxW) { m += tb[St.N + c0 + e]; sv += tb[St.N + c0 + 8 + e]; }
+                if (byH || bx0) { m += tb[2 * St.N + c0 + e]; sv += tb[2 * St.N + c0 + 8 + e]; }
+                if (byH) { m += tb[3 * St.N + c0 + e]; sv += tb[3 * St.N + c0 + 8 + e]; }
+                if (byH || bxW) { m += tb[4 * St.N + c0 + e]; sv += tb[4 * St.N + c0 + 8 + e]; }
+              }
+              const float arw_mean = p.scale * m, arw_logsd = p.scale * sv;  // models.py:282-285
+              const size_t ge = gi + (size_t)e * HW;
+              float z0 = zv[e];
+              float eps = 0.f, pls = 0.f;
+              if (MODE == IAF_MODE_LAYER) {
+                eps = z0;
+                pls = __ldg(p.post_logsd + ge);
+                z0 = fmaf(fast_exp(pls), eps, __ldg(p.post_mean + ge));
+              }
+              const float zn = (z0 - arw_mean) * fast_exp(-arw_logsd);
+              p.z_out[ge] = zn;
+              if (MODE == IAF_MODE_STEP) {
+                if (p.elem) p.elem[ge] = arw_logsd;
+                red[0] += arw_logsd;
+              } else {
+                const float logqs = -0.9189385332046727f - pls - 0.5f * eps * eps + arw_logsd;
+                const float pl = __ldg(p.prior_logsd + ge);
+                const float d = zn - __ldg(p.prior_mean + ge);
+                const float logps = -0.9189385332046727f - pl - 0.5f * d * d * fast_exp(-2.0f * pl);
+                const float kl = logqs - logps;
+                if (p.elem) p.elem[ge] = kl;
+                red[e] = kl;
+              }
+            }
+          }
+          if (MODE == IAF_MODE_LAYER) {
+            for (int nl_ = 0; nl_ < ns; ++nl_) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                float x = (si.valid && si.n == n_first + nl_) ? red[e] : 0.f;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+                if (lane == 0) s_part[((pb * 4 + qd) * p.MAXS + nl_) * p.C + ch0 + e] = x;
+              }
+            }
+          }
+        }
+        if (!waited) mbar_wait(&bars[LB_ACC_FULL + b], (uint32_t)(use & 1));
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[LB_ACC_EMPTY + b]);
+
+        if (p.persample_out || p.bc_out) {
+          constexpr bool LAY = (MODE == IAF_MODE_LAYER);
+          if (!LAY) {
+            for (int nl_ = 0; nl_ < ns; ++nl_) {
+              float x = (si.valid && si.n == n_first + nl_) ? red[0] : 0.f;
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+              if (lane == 0) s_part[(pb * LY_WORKERS + warp) * p.MAXS + nl_] = x;
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars[LB_PART + pb]);
+          if (warp == 0) {
+            mbar_wait(&bars[LB_PART + pb], (uint32_t)((i >> 1) & 1));
+            const int cred = LAY ? p.C : 1;
+            for (int k_ = lane; k_ < ns * cred; k_ += 32) {
+              float tot = 0.f;
+              if (LAY) {
+                const int nl_ = k_ / p.C, c = k_ - nl_ * p.C;
+                for (int qq = 0; qq < 4; ++qq) tot += s_part[((pb * 4 + qq) * p.MAXS + nl_) * p.C + c];
+              } else {
+                for (int w = 0; w < LY_WORKERS; ++w) tot += s_part[(pb * LY_WORKERS + w) * p.MAXS + k_];
+              }
+              p.tilepart[((size_t)u * p.MAXS) * cred + k_] = tot;
+              __threadfence();
+            }
+            __syncwarp();
+            for (int k_ = lane; k_ < ns; k_ += 32) {
+              const int n = n_first + k_;
+              const int a = n * p.SPS, bb = a + p.SPS - 1;
+              const int ta = a / TC_TILE, tbk = bb / TC_TILE;
+              const unsigned expected = (unsigned)(tbk - ta + 1);
+              __threadfence();
+              if (atomicAdd(p.counter + n, 1u) == expected - 1u) {
+                __threadfence();
+                p.counter[n] = 0u;
+                float cost = 0.f;
+                for (int c = 0; c < cred; ++c) {
+                  float tot = 0.f;
+                  for (int tt = ta; tt <= tbk; ++tt) {
+                    const int nf = fast_div(tt * TC_TILE, p.SPS, p.mg_sps);
+                    tot += __ldcg(p.tilepart + ((size_t)tt * p.MAXS + (n - nf)) * cred + c);
+                  }
+                  if (LAY && p.bc_out) p.bc_out[(size_t)n * p.C + c] = tot;
+                  cost += tot;
+                }
+                if (p.persample_out) p.persample_out[n] = LAY ? cost : -cost;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == LY_MMA_WARP) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
