@@ -69,10 +69,17 @@ struct iaf_plan {
   // host-entry staging
   float* st_z; float* st_ctx; float* st_zo; float* st_ls; float* st_ld;
   int staging_B;
+  // pipelined host entry: IAF_NSLOT device staging slots, copy-in / compute / copy-out streams
+  float* ps_z[3]; float* ps_ctx[3]; float* ps_zo[3]; float* ps_ls[3]; float* ps_ld[3];
+  cudaStream_t s_h2d, s_cmp, s_d2h;
+  cudaEvent_t ev_h2d[3], ev_cmp[3], ev_d2h[3];
+  int pipe_B;
+  uint64_t submit_idx;
   // tensor-core path
   IafTcPlan* tc;
   uint64_t launches;
 };
+#define IAF_NSLOT 3
 
 static bool simt_geometry(iaf_plan* pl, int band_rows, size_t* smem_out) {
   const iaf_desc_t& d = pl->d;
@@ -241,6 +248,16 @@ void iaf_plan_destroy(iaf_plan_t* pl) {
   if (pl->counter) cudaFree(pl->counter);
   float* st[] = {pl->st_z, pl->st_ctx, pl->st_zo, pl->st_ls, pl->st_ld};
   for (float* q : st) if (q) cudaFree(q);
+  for (int i = 0; i < IAF_NSLOT; ++i) {
+    float* ps[] = {pl->ps_z[i], pl->ps_ctx[i], pl->ps_zo[i], pl->ps_ls[i], pl->ps_ld[i]};
+    for (float* q : ps) if (q) cudaFree(q);
+    if (pl->ev_h2d[i]) cudaEventDestroy(pl->ev_h2d[i]);
+    if (pl->ev_cmp[i]) cudaEventDestroy(pl->ev_cmp[i]);
+    if (pl->ev_d2h[i]) cudaEventDestroy(pl->ev_d2h[i]);
+  }
+  if (pl->s_h2d) cudaStreamDestroy(pl->s_h2d);
+  if (pl->s_cmp) cudaStreamDestroy(pl->s_cmp);
+  if (pl->s_d2h) cudaStreamDestroy(pl->s_d2h);
   if (pl->tc) iaf_tc_plan_destroy(pl->tc);
   delete pl;
 }
@@ -398,6 +415,73 @@ int iaf_step_fwd_host(iaf_plan_t* pl, const float* z_host, const float* context_
   if (logdet_out_host)
     CK(cudaMemcpyAsync(logdet_out_host, pl->st_ld, sizeof(float) * B, cudaMemcpyDeviceToHost, stream));
   CK(cudaStreamSynchronize(stream));
+  return IAF_OK;
+}
+
+int iaf_step_submit_host(iaf_plan_t* pl, const float* z_host, const float* context_host, float* z_out_host,
+                         float* logsd_out_host, float* logdet_out_host, int B) {
+  if (!pl || !z_host || !z_out_host || B <= 0) return IAF_ERR_BAD_ARG;
+  if (pl->d.n_hidden > 0 && !context_host) return IAF_ERR_BAD_ARG;
+  const iaf_desc_t& d = pl->d;
+  const size_t hw = (size_t)d.H * d.W;
+  const size_t nz = (size_t)B * d.n_z * hw, nc = (size_t)B * (d.n_hidden ? d.hidden[0] : 1) * hw;
+  if (!pl->s_h2d) {
+    CK(cudaStreamCreateWithFlags(&pl->s_h2d, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&pl->s_cmp, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&pl->s_d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < IAF_NSLOT; ++i) {
+      CK(cudaEventCreateWithFlags(&pl->ev_h2d[i], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&pl->ev_cmp[i], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&pl->ev_d2h[i], cudaEventDisableTiming));
+    }
+  }
+  if (B > pl->pipe_B) {
+    CK(cudaDeviceSynchronize());
+    for (int i = 0; i < IAF_NSLOT; ++i) {
+      float** ps[] = {&pl->ps_z[i], &pl->ps_ctx[i], &pl->ps_zo[i], &pl->ps_ls[i], &pl->ps_ld[i]};
+      for (float** q : ps) { if (*q) cudaFree(*q); *q = nullptr; }
+      CK(cudaMalloc(&pl->ps_z[i], sizeof(float) * nz));
+      CK(cudaMalloc(&pl->ps_ctx[i], sizeof(float) * nc));
+      CK(cudaMalloc(&pl->ps_zo[i], sizeof(float) * nz));
+      CK(cudaMalloc(&pl->ps_ls[i], sizeof(float) * nz));
+      CK(cudaMalloc(&pl->ps_ld[i], sizeof(float) * B));
+    }
+    pl->pipe_B = B;
+  }
+  const int sl = (int)(pl->submit_idx % IAF_NSLOT);
+  const bool reuse = pl->submit_idx >= IAF_NSLOT;
+  // copy-in: the slot's previous step must have been computed
+  if (reuse) CK(cudaStreamWaitEvent(pl->s_h2d, pl->ev_cmp[sl], 0));
+  CK(cudaMemcpyAsync(pl->ps_z[sl], z_host, sizeof(float) * nz, cudaMemcpyHostToDevice, pl->s_h2d));
+  if (d.n_hidden > 0)
+    CK(cudaMemcpyAsync(pl->ps_ctx[sl], context_host, sizeof(float) * nc, cudaMemcpyHostToDevice, pl->s_h2d));
+  CK(cudaEventRecord(pl->ev_h2d[sl], pl->s_h2d));
+  // compute: inputs landed, the slot's previous outputs already copied out
+  CK(cudaStreamWaitEvent(pl->s_cmp, pl->ev_h2d[sl], 0));
+  if (reuse) CK(cudaStreamWaitEvent(pl->s_cmp, pl->ev_d2h[sl], 0));
+  int st = iaf_step_fwd(pl, pl->ps_z[sl], pl->ps_ctx[sl], pl->ps_zo[sl], logsd_out_host ? pl->ps_ls[sl] : nullptr,
+                        logdet_out_host ? pl->ps_ld[sl] : nullptr, B, (void*)pl->s_cmp);
+  if (st != IAF_OK) return st;
+  CK(cudaEventRecord(pl->ev_cmp[sl], pl->s_cmp));
+  // copy-out
+  CK(cudaStreamWaitEvent(pl->s_d2h, pl->ev_cmp[sl], 0));
+  CK(cudaMemcpyAsync(z_out_host, pl->ps_zo[sl], sizeof(float) * nz, cudaMemcpyDeviceToHost, pl->s_d2h));
+  if (logsd_out_host)
+    CK(cudaMemcpyAsync(logsd_out_host, pl->ps_ls[sl], sizeof(float) * nz, cudaMemcpyDeviceToHost, pl->s_d2h));
+  if (logdet_out_host)
+    CK(cudaMemcpyAsync(logdet_out_host, pl->ps_ld[sl], sizeof(float) * B, cudaMemcpyDeviceToHost, pl->s_d2h));
+  CK(cudaEventRecord(pl->ev_d2h[sl], pl->s_d2h));
+  pl->submit_idx += 1;
+  return IAF_OK;
+}
+
+int iaf_host_wait(iaf_plan_t* pl) {
+  if (!pl) return IAF_ERR_BAD_ARG;
+  if (pl->s_d2h) {
+    CK(cudaStreamSynchronize(pl->s_h2d));
+    CK(cudaStreamSynchronize(pl->s_cmp));
+    CK(cudaStreamSynchronize(pl->s_d2h));
+  }
   return IAF_OK;
 }
 

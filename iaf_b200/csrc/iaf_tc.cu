@@ -33,6 +33,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -43,7 +44,11 @@
 #define TC_THREADS (TC_WTHREADS + 32)
 #define TC_CTRL_WARP TC_WORKERS
 #define TC_TILE 128
+#ifdef IAF_TC_TIMELINE
+#define TC_SMEM_LIMIT (227 * 1024 - 2048 - 6144)  // room for the static event buffers
+#else
 #define TC_SMEM_LIMIT (227 * 1024 - 2048)
+#endif
 #define TC_NGROUPS 1   // 1: all 16 worker warps run every phase together; 2: two ping-pong groups by tile parity
 #define TC_GWARPS (TC_WORKERS / TC_NGROUPS)
 #define TC_GTHREADS (TC_GWARPS * 32)
@@ -231,7 +236,7 @@ __device__ __forceinline__ void split_store8(const float* v, uint8_t* hi_ptr, ui
 // Optional in-kernel timeline (compile with -DIAF_TC_TIMELINE; development aid only): CTA 0 records
 // (tag, tile, clock) triples for the control lane and lane 0 of the first warp of each worker group.
 #ifdef IAF_TC_TIMELINE
-#define TL_MAX 128
+#define TL_MAX 64
 __device__ long long g_tl[3][TL_MAX][3];
 __device__ int g_tl_n[3];
 // events are staged in shared memory (a global counter would cost an L2 round trip per event)
@@ -512,17 +517,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
             uint32_t r[16];
             tmem_ld16(t_acc + (uint32_t)c0, r);
             tmem_ld_wait();
-            float v[16];
+float v[16];
+            {
+              // branch-free: bias rows come in as 16-byte vectors, the pad-channel terms (conv.py:77-83: the pad
+              // channel is 1 where a tap falls outside the image) are 0/1-weighted FMAs, and an invalid slot
+              // (pad column, zero row, past the end) is multiplied to zero: that zero IS the conv's padding
+              const float4* tb4 = reinterpret_cast<const float4*>(tb + c0);
+              float bsv[16];
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              float a = __uint_as_float(r[e]) + tb[c0 + e] + cx[e];
-              if (PADW) {  // pad channel = 1 where the tap falls outside the image (conv.py:77-83)
-                if (bxW) a += tb[St.N + c0 + e];
-                if (byH || bx0) a += tb[2 * St.N + c0 + e];
-                if (byH) a += tb[3 * St.N + c0 + e];
-                if (byH || bxW) a += tb[4 * St.N + c0 + e];
+              for (int e4 = 0; e4 < 4; ++e4) {
+                const float4 t4 = tb4[e4];
+                bsv[4 * e4] = t4.x; bsv[4 * e4 + 1] = t4.y; bsv[4 * e4 + 2] = t4.z; bsv[4 * e4 + 3] = t4.w;
               }
-              v[e] = si.valid ? tc_apply_nl<NLT>(a, p.nl) : 0.f;
+              if (PADW) {
+                const float f1 = bxW ? 1.f : 0.f, f2 = (byH || bx0) ? 1.f : 0.f, f3 = byH ? 1.f : 0.f,
+                            f4 = (byH || bxW) ? 1.f : 0.f;
+#pragma unroll
+                for (int e = 0; e < 16; ++e)
+                  bsv[e] += f1 * tb[St.N + c0 + e] + f2 * tb[2 * St.N + c0 + e] + f3 * tb[3 * St.N + c0 + e] +
+                            f4 * tb[4 * St.N + c0 + e];
+              }
+              const float validf = si.valid ? 1.f : 0.f;
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                const float a = __uint_as_float(r[e]) + bsv[e] + cx[e];
+                float o;
+                if (NLT == IAF_NL_ELU) {
+                  const float ex = fast_exp(fminf(a, 0.f)) - 1.0f;  // elu, exp always evaluated: no divergence
+                  o = a < 0.f ? ex : a;
+                } else {
+                  o = tc_apply_nl<NLT>(a, p.nl);
+                }
+                v[e] = o * validf;
+              }
             }
 #pragma unroll
             for (int hch = 0; hch < 2; ++hch) {
@@ -712,7 +739,7 @@ struct TcPackLayer {
 };
 struct TcPackParams {
   TcPackLayer layer[IAF_MAX_HIDDEN + IAF_MAX_HEADS];
-  int n_layers, variant;
+  int n_layers, variant, korder;
 };
 
 __device__ __forceinline__ bool tc_centre_visible(int ci, int co, int cin, int cout, int zd) {
@@ -767,7 +794,8 @@ __global__ void __launch_bounds__(128) iaf_tc_pack_kernel(const __grid_constant_
       float v = tc_raw_weight(L, p.variant, t, ci, co);
       if (t == 0 && !tc_centre_visible(ci, co, L.cin, L.cout, L.zerodiag)) v = 0.f;
       v *= factor;
-      const int k = t * L.cin + ci;
+      // K order: fused kernel [tap][ci]; layer-at-a-time kernel [ci / 16][tap][ci % 16]
+      const int k = p.korder ? (((ci >> 4) * IAF_NTAPS + t) * 16 + (ci & 15)) : (t * L.cin + ci);
       const size_t o = ((size_t)(k >> 3) * L.N + col) * 8 + (k & 7);
       const __nv_bfloat16 h = __float2bfloat16_rn(v);
       L.whi[o] = h;
@@ -797,6 +825,7 @@ struct IafTcPlan {
   bool layer_ok;             // the per-(sample,channel) scratch of the fused-layer mode fits
   // layer-at-a-time mode (hidden widths that do not fit the fused kernel's on-chip rings)
   bool layered;
+  int ly_stage[IAF_MAX_STAGES];
   int ly_NB[IAF_MAX_STAGES], ly_sm_a[IAF_MAX_STAGES], ly_sm_b[IAF_MAX_STAGES], ly_sm_bias[IAF_MAX_STAGES],
       ly_sm_part[IAF_MAX_STAGES], ly_tmem[IAF_MAX_STAGES];
   size_t ly_smem[IAF_MAX_STAGES];
@@ -921,14 +950,16 @@ static bool ly_layout(const iaf_desc_t* d, IafTcPlan* pl) {
     q->K[j] = IAF_NTAPS * prev;
     prev = q->N[j];
     int off = 0;
-    q->ly_sm_a[j] = off; off += 2 * (q->cin[j] / 8) * q->WIN * 16;
+    // first stage: the workers build the whole A window from fp32 z; later stages stream A chunk pairs with the weights
+    q->ly_sm_a[j] = off; if (j == 0) off += 2 * (q->cin[j] / 8) * q->WIN * 16;
     q->ly_sm_bias[j] = off; off += 5 * q->N[j] * 4;
     off = tc_round_up(off, 16);
     q->ly_sm_part[j] = off;
     off += std::max(2 * LY_WORKERS * q->MAXS * 4, 2 * 4 * q->MAXS * d->n_z * 4);
     off = tc_round_up(off, 128);
     q->ly_sm_b[j] = off;
-    const int slot = 2 * LY_KC * 2 * q->N[j] * 16;  // hi + lo halves of one ring slot
+    const int slot = 2 * LY_KC * 2 * q->N[j] * 16 + (j ? 4 * q->WIN * 16 : 0);  // weight chunk hi+lo (+ A chunk pair hi+lo)
+    q->ly_stage[j] = slot;
     int nb = (TC_SMEM_LIMIT - off) / slot;
     if (nb < 2) return false;
     q->ly_NB[j] = std::min(nb, LY_MAX_NB);
@@ -949,7 +980,8 @@ int iaf_tc_plan_create(IafTcPlan** out, const iaf_desc_t* d) {
   memset(pl, 0, sizeof(*pl));
   pl->d = *d;
   pl->layered = false;
-  if (!tc_layout(d, pl)) {
+  const char* force = getenv("IAF_TC_FORCE_LAYERED");  // development switch: compare the two tensor-core schedules
+  if ((force && force[0] == '1') || !tc_layout(d, pl)) {
     if (!ly_layout(d, pl)) { delete pl; return IAF_ERR_UNSUPPORTED; }
     pl->layered = true;
   }
@@ -1008,6 +1040,7 @@ int iaf_tc_pack(IafTcPlan* pl, const float* const* w, const float* const* scale,
   memset(&pp, 0, sizeof(pp));
   pp.n_layers = d.n_hidden + d.n_heads;
   pp.variant = d.variant;
+  pp.korder = pl->layered ? 1 : 0;
   int max_cout = 0;
   for (int j = 0; j < pl->n_stages; ++j) {
     const size_t wb = (size_t)pl->K[j] * pl->N[j] * 2;
@@ -1136,7 +1169,9 @@ int iaf_tc_run(IafTcPlan* pl, const IafTcArgs* a, cudaStream_t stream, int* n_la
       q.NB = pl->ly_NB[j];
       q.sm_a = pl->ly_sm_a[j]; q.sm_b = pl->ly_sm_b[j]; q.sm_bias = pl->ly_sm_bias[j]; q.sm_part = pl->ly_sm_part[j];
       q.b_chunk_bytes = LY_KC * 2 * pl->N[j] * 16;
+      q.stage_bytes = pl->ly_stage[j];
       q.n_bchunks = (pl->K[j] / 16) / LY_KC;
+      { const char* tls = getenv("IAF_TL_STAGE"); q.tl_enable = tls ? (atoi(tls) == j) : (j == pl->n_stages - 1); }
       lk<<<grid, LY_THREADS, pl->ly_smem[j], stream>>>(q);
     }
     if (n_launches) *n_launches = pl->n_stages;

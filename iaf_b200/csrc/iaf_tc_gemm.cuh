@@ -24,8 +24,11 @@
 #define LY_KC 5        // K-steps (of 16) per weight chunk
 #define LY_MAX_NB 6
 
-enum { LB_AFULL = 0, LB_AEMPTY = 1, LB_ACC_FULL = 2, LB_ACC_EMPTY = 4, LB_BFULL = 6, LB_BEMPTY = 6 + LY_MAX_NB,
-       LB_PART = 6 + 2 * LY_MAX_NB, LB_COUNT = 8 + 2 * LY_MAX_NB };
+#define LY_MAX_KS 16   // K-steps per tap (Cin / 16), Cin <= 256
+enum { LB_ACC_FULL = 0, LB_ACC_EMPTY = 2, LB_BFULL = 4, LB_BEMPTY = 4 + LY_MAX_NB, LB_PART = 4 + 2 * LY_MAX_NB,
+       LB_AFULL = 6 + 2 * LY_MAX_NB,                 // + K-step: chunk pair (2ks, 2ks+1) of the A window has landed
+       LB_AEMPTY = 6 + 2 * LY_MAX_NB + LY_MAX_KS,    // + K-step: the MMAs of that chunk pair are done
+       LB_COUNT = 6 + 2 * LY_MAX_NB + 2 * LY_MAX_KS };
 
 struct IafLyParams {
   IafTcParams t;               // geometry, pointers, slot decoding (t.st[0] describes THIS stage)
@@ -39,8 +42,10 @@ struct IafLyParams {
   int first;                   // 1: first stage (adds the context)
   int NB;                      // weight ring depth
   int sm_a, sm_b, sm_bias, sm_part;
+  int stage_bytes;             // bytes of one ring stage: 2 * b_chunk_bytes (+ 4 * WIN * 16 when the A pair rides along)
   int b_chunk_bytes;           // bytes of one ring slot half (hi or lo): LY_KC * 2 * N * 16
   int n_bchunks;               // weight chunks per tile
+  int tl_enable;               // timeline builds only: this launch flushes its events
 };
 
 template <bool PADW, int MODE, int NLT, int THW>
@@ -50,6 +55,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) iaf_ly_kernel(const __grid_cons
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bars[LB_COUNT];
   __shared__ uint32_t s_tmem;
+  TL_DECL
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const IafTcStage& St = p.st[0];
@@ -58,12 +64,15 @@ __global__ void __launch_bounds__(LY_THREADS, 1) iaf_ly_kernel(const __grid_cons
   const int a_lo_off = nchunk * a_plane;
   const int n_my = (p.NT - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // tiles of this CTA
   const int acc_cols = St.N;
+  const bool resident = q.n_bchunks <= q.NB;
 
   if (warp == LY_MMA_WARP) {
     tmem_alloc(&s_tmem, (uint32_t)p.tmem_cols);
     if (lane == 0) {
-      mbar_init(&bars[LB_AFULL], q.in_mode ? 1 : LY_WORKERS);
-      mbar_init(&bars[LB_AEMPTY], 1);
+      for (int i = 0; i < LY_MAX_KS; ++i) {
+        mbar_init(&bars[LB_AFULL + i], q.in_mode ? 1 : LY_WORKERS);
+        mbar_init(&bars[LB_AEMPTY + i], 1);
+      }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&bars[LB_ACC_FULL + i], 1);
         mbar_init(&bars[LB_ACC_EMPTY + i], LY_WORKERS);
@@ -95,76 +104,94 @@ __global__ void __launch_bounds__(LY_THREADS, 1) iaf_ly_kernel(const __grid_cons
       int gchunk = 0;
       for (int i = 0; i < n_my; ++i) {
         const int u = (int)blockIdx.x + i * (int)gridDim.x;
-        if (q.in_mode) {
-          if (i >= 1) mbar_wait(&bars[LB_AEMPTY], (uint32_t)((i - 1) & 1));
-          mbar_expect_tx(&bars[LB_AFULL], (uint32_t)(2 * nchunk * a_plane));
-          for (int c = 0; c < nchunk; ++c) {
-            const size_t go = ((size_t)c * q.S_pad + (size_t)u * TC_TILE) * 8;
-            bulk_g2s(smem + q.sm_a + c * a_plane, q.a_hi + go, (uint32_t)a_plane, &bars[LB_AFULL]);
-            bulk_g2s(smem + q.sm_a + a_lo_off + c * a_plane, q.a_lo + go, (uint32_t)a_plane, &bars[LB_AFULL]);
-          }
-        }
-        for (int c = 0; c < q.n_bchunks; ++c, ++gchunk) {
+        // K order is [K-step within a tap][tap]: weight chunk c and A chunk pair (2c, 2c+1) are consumed together,
+        // so both stream through shared memory at the pace of the MMAs
+        for (int c = 0; c < q.n_bchunks; ++c) {
+          if (resident && i >= 1 && !q.in_mode) continue;  // weights already resident, A comes from the workers
           const int stg = gchunk % q.NB;
           const int use = gchunk / q.NB;
           if (use >= 1) mbar_wait(&bars[LB_BEMPTY + stg], (uint32_t)((use - 1) & 1));
-          mbar_expect_tx(&bars[LB_BFULL + stg], (uint32_t)(2 * q.b_chunk_bytes));
+          uint8_t* dst = smem + q.sm_b + stg * q.stage_bytes;
           const size_t bo = (size_t)c * q.b_chunk_bytes;
-          uint8_t* dst = smem + q.sm_b + stg * 2 * q.b_chunk_bytes;
+          if (q.in_mode) {
+            // one ring stage = A chunk pair (hi c0, hi c1, lo c0, lo c1) + the weight chunk (hi, lo) of K-step c
+            mbar_expect_tx(&bars[LB_BFULL + stg], (uint32_t)(4 * a_plane + 2 * q.b_chunk_bytes));
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const size_t go = ((size_t)(2 * c + h) * q.S_pad + (size_t)u * TC_TILE) * 8;
+              bulk_g2s(dst + h * a_plane, q.a_hi + go, (uint32_t)a_plane, &bars[LB_BFULL + stg]);
+              bulk_g2s(dst + (2 + h) * a_plane, q.a_lo + go, (uint32_t)a_plane, &bars[LB_BFULL + stg]);
+            }
+            dst += 4 * a_plane;
+          } else {
+            mbar_expect_tx(&bars[LB_BFULL + stg], (uint32_t)(2 * q.b_chunk_bytes));
+          }
           bulk_g2s(dst, reinterpret_cast<const uint8_t*>(St.whi) + bo, (uint32_t)q.b_chunk_bytes, &bars[LB_BFULL + stg]);
           bulk_g2s(dst + q.b_chunk_bytes, reinterpret_cast<const uint8_t*>(St.wlo) + bo, (uint32_t)q.b_chunk_bytes,
                    &bars[LB_BFULL + stg]);
+          ++gchunk;
         }
       }
     }
     __syncwarp();
   } else if (warp == LY_MMA_WARP) {
     // ===================== MMA issue (convergent warp, one elected lane) =====================
-    const int ks_per_tap = St.cin >> 4;
     const uint32_t idesc = umma_idesc(St.N);
     const uint32_t a_base = smem_u32(smem + q.sm_a);
     const uint32_t b_plane = (uint32_t)St.N * 16u;
+    // slot shifts of the taps (0,0) (0,+1) (+1,-1) (+1,0) (+1,+1), in 16-byte descriptor units
+    const uint32_t sh1 = 1u, sh2 = (uint32_t)(p.Wp - 1), sh3 = (uint32_t)p.Wp, sh4 = (uint32_t)(p.Wp + 1);
+    const uint32_t a_kstep = (2u * (uint32_t)a_plane) >> 4, b_tstep = (2u * b_plane) >> 4;
+    const uint32_t ah_base = umma_desc_lo(a_base, (uint32_t)a_plane);
+    const uint32_t al_base = umma_desc_lo(a_base + (uint32_t)a_lo_off, (uint32_t)a_plane);
     int gchunk = 0;
     for (int i = 0; i < n_my; ++i) {
       const int b = i & 1, use = i >> 1;
-      mbar_wait(&bars[LB_AFULL], (uint32_t)(i & 1));
       if (use >= 1) mbar_wait(&bars[LB_ACC_EMPTY + b], (uint32_t)((use - 1) & 1));
       tc_fence_after();
+      if (lane == 0) TL(0, 100, i);
       const uint32_t d_tmem = tmem_base + (uint32_t)(b * acc_cols);
-      uint32_t acc = 0;
-      int kstep = 0;
-      for (int c = 0; c < q.n_bchunks; ++c, ++gchunk) {
-        const int stg = gchunk % q.NB;
-        mbar_wait(&bars[LB_BFULL + stg], (uint32_t)((gchunk / q.NB) & 1));
+      for (int c = 0; c < q.n_bchunks; ++c) {
+        const bool res = resident && !q.in_mode;
+        const int stg = res ? c : gchunk % q.NB;
+        if (!q.in_mode) mbar_wait(&bars[LB_AFULL + c], (uint32_t)(i & 1));
+        mbar_wait(&bars[LB_BFULL + stg], res ? 0u : (uint32_t)((gchunk / q.NB) & 1));
         tc_fence_after();
-        const uint32_t bh0 = smem_u32(smem + q.sm_b + stg * 2 * q.b_chunk_bytes);
-        const uint32_t bl0 = bh0 + (uint32_t)q.b_chunk_bytes;
+        const uint32_t sbase = smem_u32(smem + q.sm_b + stg * q.stage_bytes);
+        uint32_t ah0, al0, bbase;
+        if (q.in_mode) {  // operands of this K-step both live in the ring stage
+          ah0 = umma_desc_lo(sbase, (uint32_t)a_plane);
+          al0 = umma_desc_lo(sbase + 2u * (uint32_t)a_plane, (uint32_t)a_plane);
+          bbase = sbase + 4u * (uint32_t)a_plane;
+        } else {
+          ah0 = ah_base + (uint32_t)c * a_kstep;
+          al0 = al_base + (uint32_t)c * a_kstep;
+          bbase = sbase;
+        }
+        const uint32_t bh0 = umma_desc_lo(bbase, b_plane);
+        const uint32_t bl0 = umma_desc_lo(bbase + (uint32_t)q.b_chunk_bytes, b_plane);
+        const uint32_t acc0 = c ? 1u : 0u;
         if (elect_one_sync()) {
-#pragma unroll
-          for (int kk = 0; kk < LY_KC; ++kk) {
-            const int ksg = kstep + kk;
-            const int tp = ksg / ks_per_tap, ks = ksg - tp * ks_per_tap;
-            const int shift = (tp < 2) ? tp : p.Wp + tp - 3;  // taps (0,0) (0,+1) (+1,-1) (+1,0) (+1,+1)
-            const uint32_t a_off = (uint32_t)shift * 16u + (uint32_t)(ks * 2) * (uint32_t)a_plane;
-            const uint32_t ah = umma_desc_lo(a_base + a_off, (uint32_t)a_plane);
-            const uint32_t al = umma_desc_lo(a_base + (uint32_t)a_lo_off + a_off, (uint32_t)a_plane);
-            const uint32_t bh = umma_desc_lo(bh0 + (uint32_t)(kk * 2) * b_plane, b_plane);
-            const uint32_t bl = umma_desc_lo(bl0 + (uint32_t)(kk * 2) * b_plane, b_plane);
-            umma_bf16(d_tmem, mk_desc(al), mk_desc(bh), idesc, acc);  // lo * hi
-            acc = 1;
-            umma_bf16(d_tmem, mk_desc(ah), mk_desc(bl), idesc, acc);  // hi * lo
-            umma_bf16(d_tmem, mk_desc(ah), mk_desc(bh), idesc, acc);  // hi * hi
+#define LY_TAP(T, SH, ACC)                                                                   \
+          umma_bf16(d_tmem, mk_desc(al0 + (SH)), mk_desc(bh0 + (T) * b_tstep), idesc, (ACC)); \
+          umma_bf16(d_tmem, mk_desc(ah0 + (SH)), mk_desc(bl0 + (T) * b_tstep), idesc, 1u);    \
+          umma_bf16(d_tmem, mk_desc(ah0 + (SH)), mk_desc(bh0 + (T) * b_tstep), idesc, 1u);
+          LY_TAP(0u, 0u, acc0)
+          LY_TAP(1u, sh1, 1u)
+          LY_TAP(2u, sh2, 1u)
+          LY_TAP(3u, sh3, 1u)
+          LY_TAP(4u, sh4, 1u)
+#undef LY_TAP
+          if (!res) umma_commit(&bars[LB_BEMPTY + stg]);
+          if (!q.in_mode) umma_commit(&bars[LB_AEMPTY + c]);
+          if (c == q.n_bchunks - 1) {
+            umma_commit(&bars[LB_ACC_FULL + b]);
+            TL(0, 200, i);
           }
-          umma_commit(&bars[LB_BEMPTY + stg]);
         }
         __syncwarp();
-        kstep += LY_KC;
+        if (!res) ++gchunk;
       }
-      if (elect_one_sync()) {
-        umma_commit(&bars[LB_ACC_FULL + b]);
-        umma_commit(&bars[LB_AEMPTY]);
-      }
-      __syncwarp();
     }
   } else {
     // ===================== workers: (first stage) z -> operand window; epilogues =====================
@@ -204,7 +231,9 @@ __global__ void __launch_bounds__(LY_THREADS, 1) iaf_ly_kernel(const __grid_cons
           }
         }
       }
-      if (i >= 1) mbar_wait(&bars[LB_AEMPTY], (uint32_t)((i - 1) & 1));
+      if (warp == 0 && lane == 0) TL(1, 30, i);
+      if (i >= 1) mbar_wait(&bars[LB_AEMPTY + q.n_bchunks - 1], (uint32_t)((i - 1) & 1));  // commits are in order
+      if (warp == 0 && lane == 0) TL(1, 31, i);
 #pragma unroll
       for (int it = 0; it < TC_ZITEMS; ++it) {
         if (dsto[it] >= 0) {
@@ -214,7 +243,8 @@ __global__ void __launch_bounds__(LY_THREADS, 1) iaf_ly_kernel(const __grid_cons
       }
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars[LB_AFULL]);
+      if (lane == 0)
+        for (int c = 0; c < q.n_bchunks; ++c) mbar_arrive(&bars[LB_AFULL + c]);
     };
 
     if (!q.in_mode && n_my > 0) load_window(0);
@@ -225,39 +255,71 @@ __global__ void __launch_bounds__(LY_THREADS, 1) iaf_ly_kernel(const __grid_cons
       const SlotInfo si = decode_slot(p, u * TC_TILE + sl, HW);
       const bool bx0 = (si.x == 0), bxW = (si.x == p.W - 1), byH = (si.y == p.H - 1);
       const uint32_t t_acc = t_lane + (uint32_t)(b * acc_cols);
+      if (warp == 0 && lane == 0) TL(1, 10, i);
 
       if (!q.is_heads) {
         bool waited = false;
+        // context of the NEXT column group is fetched while the current one is computed
+        float cxn[16];
+        auto fetch_ctx = [&](int g) {
+          if (q.first && si.valid && g < ngroups) {  // += context   (ar.py:402 / layers.py:163)
+            const float* cp = p.ctx + ((size_t)si.n * St.N + g * 16) * HW + si.gp;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) cxn[e] = __ldg(cp + (size_t)e * HW);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) cxn[e] = 0.f;
+          }
+        };
+        fetch_ctx(cg);
         for (int g = cg; g < ngroups; g += CGS) {
           const int c0 = g * 16;
           float cx[16];
-          if (q.first && si.valid) {  // += context   (ar.py:402 / layers.py:163)
-            const float* cp = p.ctx + ((size_t)si.n * St.N + c0) * HW + si.gp;
 #pragma unroll
-            for (int e = 0; e < 16; ++e) cx[e] = __ldg(cp + (size_t)e * HW);
-          } else {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) cx[e] = 0.f;
-          }
+          for (int e = 0; e < 16; ++e) cx[e] = cxn[e];
+          fetch_ctx(g + CGS);
           if (!waited) {
             mbar_wait(&bars[LB_ACC_FULL + b], (uint32_t)(use & 1));
             tc_fence_after();
             waited = true;
+            if (warp == 0 && lane == 0) TL(1, 50, i);
           }
           uint32_t r[16];
           tmem_ld16(t_acc + (uint32_t)c0, r);
           tmem_ld_wait();
-          float v[16];
+float v[16];
+          {
+            // branch-free: bias rows come in as 16-byte vectors, the pad-channel terms (conv.py:77-83: the pad
+            // channel is 1 where a tap falls outside the image) are 0/1-weighted FMAs, and an invalid slot
+            // (pad column, zero row, past the end) is multiplied to zero: that zero IS the conv's padding
+            const float4* tb4 = reinterpret_cast<const float4*>(tb + c0);
+            float bsv[16];
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            float a = __uint_as_float(r[e]) + tb[c0 + e] + cx[e];
-            if (PADW) {
-              if (bxW) a += tb[St.N + c0 + e];
-              if (byH || bx0) a += tb[2 * St.N + c0 + e];
-              if (byH) a += tb[3 * St.N + c0 + e];
-              if (byH || bxW) a += tb[4 * St.N + c0 + e];
+            for (int e4 = 0; e4 < 4; ++e4) {
+              const float4 t4 = tb4[e4];
+              bsv[4 * e4] = t4.x; bsv[4 * e4 + 1] = t4.y; bsv[4 * e4 + 2] = t4.z; bsv[4 * e4 + 3] = t4.w;
             }
-            v[e] = si.valid ? tc_apply_nl<NLT>(a, p.nl) : 0.f;
+            if (PADW) {
+              const float f1 = bxW ? 1.f : 0.f, f2 = (byH || bx0) ? 1.f : 0.f, f3 = byH ? 1.f : 0.f,
+                          f4 = (byH || bxW) ? 1.f : 0.f;
+#pragma unroll
+              for (int e = 0; e < 16; ++e)
+                bsv[e] += f1 * tb[St.N + c0 + e] + f2 * tb[2 * St.N + c0 + e] + f3 * tb[3 * St.N + c0 + e] +
+                          f4 * tb[4 * St.N + c0 + e];
+            }
+            const float validf = si.valid ? 1.f : 0.f;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const float a = __uint_as_float(r[e]) + bsv[e] + cx[e];
+              float o;
+              if (NLT == IAF_NL_ELU) {
+                const float ex = fast_exp(fminf(a, 0.f)) - 1.0f;  // elu, exp always evaluated: no divergence
+                o = a < 0.f ? ex : a;
+              } else {
+                o = tc_apply_nl<NLT>(a, p.nl);
+              }
+              v[e] = o * validf;
+            }
           }
 #pragma unroll
           for (int hch = 0; hch < 2; ++hch) {
@@ -269,6 +331,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) iaf_ly_kernel(const __grid_cons
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[LB_ACC_EMPTY + b]);
+        if (warp == 0 && lane == 0) TL(1, 20, i);
       } else {
         // ---------------- heads: identical arithmetic to iaf_tc_kernel's last stage ----------------
         constexpr int NRED = (MODE == IAF_MODE_LAYER) ? 8 : 1;
@@ -295,6 +358,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) iaf_ly_kernel(const __grid_cons
             mbar_wait(&bars[LB_ACC_FULL + b], (uint32_t)(use & 1));
             tc_fence_after();
             waited = true;
+            if (warp == 0 && lane == 0) TL(1, 50, i);
           }
           uint32_t r[16];
           tmem_ld16(t_acc + (uint32_t)c0, r);
@@ -413,5 +477,6 @@ __global__ void __launch_bounds__(LY_THREADS, 1) iaf_ly_kernel(const __grid_cons
 
   tc_fence_before();
   __syncthreads();
+  if (q.tl_enable) { TL_FLUSH }
   if (warp == LY_MMA_WARP) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }

@@ -189,6 +189,23 @@ class IAFOperator(object):
                                                _ptr(logdet_out), B, _stream(device)))
         return z_out, logsd_out, logdet_out
 
+    def submit_host(self, z, context, z_out, logsd_out, logdet_out):
+        """Pipelined host entry: enqueue H2D + step + D2H of one batch and return at once (pinned CPU tensors,
+        valid until wait_host()).  Consecutive batches overlap copy-in, compute and copy-out."""
+        for t in (z, context, z_out, logsd_out, logdet_out):
+            if t is not None and (t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or not t.is_pinned()):
+                raise ValueError("submit_host takes pinned contiguous float32 CPU tensors")
+        B, _, H, W = z.shape
+        device = torch.device("cuda", torch.cuda.current_device())
+        self._host_plan = self._plan(H, W, device)
+        torch.cuda.current_stream(device).synchronize()  # weights packed on the caller's stream are visible
+        _lib.check(self._lib.iaf_step_submit_host(self._host_plan, _ptr(z), _ptr(context), _ptr(z_out), _ptr(logsd_out),
+                                                  _ptr(logdet_out), B))
+
+    def wait_host(self):
+        if getattr(self, "_host_plan", None) is not None:
+            _lib.check(self._lib.iaf_host_wait(self._host_plan))
+
     def layer(self, eps, post_mean, post_logsd, prior_mean, prior_logsd, context, want_kl=True):
         """Fused posterior-sample -> IAF step -> KL block (tf_train.py:56-85, models.py:273-328).
         Returns (z', kl [B,C,H,W] or None, kl_bc [B,C], kl_cost [B])."""

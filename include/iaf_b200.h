@@ -120,6 +120,16 @@ int iaf_step_fwd_host(iaf_plan_t* plan, const float* z_host, const float* contex
                       void* stream);
 
 /*
+ * Pipelined form of the host entry for back-to-back batches: enqueues copy-in, the step and
+ * copy-out of one batch on three internal streams (three device staging slots, so the H2D of batch
+ * i+1, the kernel of batch i and the D2H of batch i-1 overlap: PCIe is full duplex) and returns
+ * immediately.  Host buffers must be pinned and stay valid until iaf_host_wait() returns.
+ */
+int iaf_step_submit_host(iaf_plan_t* plan, const float* z_host, const float* context_host,
+                         float* z_out_host, float* logsd_out_host, float* logdet_out_host, int B);
+int iaf_host_wait(iaf_plan_t* plan);
+
+/*
  * The stochastic-layer block around the step, fused:
  *   tf_train.py:56-85 / models.py:273-298: posterior sample from the given noise, logqs,
  *   the IAF step, prior logps at z', kl = logqs - logps and its reductions.

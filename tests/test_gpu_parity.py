@@ -257,3 +257,14 @@ def test_step_host_entry_matches_device_entry():
     ho2 = torch.empty(B, n_z, H, W)
     op.step_host(torch.from_numpy(z), torch.from_numpy(ctx), ho2, None, None)
     assert torch.equal(ho2, ho)
+    # pipelined submission: 7 batches through 3 staging slots, every result equals the device entry
+    outs = []
+    for i in range(7):
+        zi = (torch.from_numpy(z) + 0.01 * i).pin_memory()
+        o = [torch.empty_like(hz).pin_memory(), torch.empty_like(hz).pin_memory(), torch.empty(B).pin_memory()]
+        op.submit_host(zi, hc, o[0], o[1], o[2])
+        outs.append((zi, o))
+    op.wait_host()
+    for zi, o in outs:
+        ref = op.step(zi.cuda(), torch.from_numpy(ctx).cuda())
+        assert torch.equal(o[0], ref[0].cpu()) and torch.equal(o[1], ref[1].cpu()) and torch.equal(o[2], ref[2].cpu())

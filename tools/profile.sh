@@ -11,7 +11,7 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --cs
   --log-file gpurun_out/launches_${WL}_${TAG}.csv \
   python bench.py --workload ${WL} --steps 10 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/launches_${WL}_${TAG}.log 2>&1
 # the step kernel, once, full set (skip the warm-up launches of that kernel)
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:'iaf_(tc|simt|gemm)' -s 5 -c 1 -f \
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:'iaf_(tc|simt|ly)_kernel' -s 5 -c 1 -f \
   -o gpurun_out/prof_${WL}_${TAG} \
   python bench.py --workload ${WL} --steps 10 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/prof_${WL}_${TAG}.log 2>&1
 ls -la gpurun_out | tail -5
