@@ -284,9 +284,11 @@ def main():
     if sampler:
         sampler.start()
         sampler.phase = "warmup"
+    lc0 = op.launch_count()
     for i in range(Wm):
         launch(i, stream)
     torch.cuda.synchronize()
+    launches_per_step = (op.launch_count() - lc0) // Wm  # 1 (fused / SIMT kernel) or one per conv stage (layered)
 
     graph = None
     launch_mode = "direct"
@@ -336,7 +338,7 @@ def main():
         dist.barrier()
     if sampler:
         sampler.phase = "between"
-    n_launched = K if graph is not None else op.launch_count() - launches0
+    n_launched = K * launches_per_step if graph is not None else op.launch_count() - launches0
     t_kernels_ms = ev0.elapsed_time(ev1)
     t_total_ms = ev0.elapsed_time(ev2)
     tt = torch.tensor([t_total_ms, t_kernels_ms], device=device, dtype=torch.float64)
@@ -426,7 +428,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": "%s: single IAF step, n_z=%d hidden=%s %dx%d batch %d per GPU, TF-variant numerics" %
                    (name, n_z, hidden, H, W, B), "global_batch": B * world, "parallelism": "dp%d" % world,
-                   "path": op.path_used(H, W, device), "launch": launch_mode,
+                   "path": op.path_used(H, W, device), "launch": launch_mode, "kernels_per_step": launches_per_step,
                    "l2": "rotating %d input/output sets (%.0f MB > 126 MB L2)" % (nsets, nsets * alg_bytes_unit / 2 ** 20),
                    "collective": "one all-reduce of the scalar sum(logdet) per timed region" if world > 1 else "none",
                    "samples_per_s": value / (n_z * H * W)},
