@@ -16,7 +16,8 @@ def shard_range(n, rank, world):
 
 def allreduce_scalars(values, group=None):
     """Sum-all-reduce a short list of scalar tensors in ONE collective (NCCL on GPU, gloo on CPU)."""
-    buf = torch.stack([v.reshape(()).to(torch.float32) for v in values])
+    dtype = torch.float64 if any(v.dtype == torch.float64 for v in values) else torch.float32
+    buf = torch.stack([v.reshape(()).to(dtype) for v in values])
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
     return list(buf.unbind(0))

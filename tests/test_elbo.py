@@ -1,0 +1,94 @@
+"""bits/dim parity (BASELINE.json metric): the restated ELBO forward evaluated with the B200
+operator equals the same forward evaluated with the oracle operator on identical weights, inputs and noise."""
+import numpy as np
+import pytest
+import torch
+
+from iaf_b200 import elbo
+from oracle import iaf_oracle as O
+from oracle.elbo_oracle import OracleIAF
+
+
+def _setup(hps, B, seed, dtype, device):
+    p = elbo.make_params(hps, seed=seed)
+    params = {k: torch.from_numpy(np.asarray(v)).to(dtype).to(device) for k, v in p.items()}
+    rng = np.random.RandomState(seed + 1)
+    x = torch.from_numpy(rng.randint(0, 256, size=(B, 3, hps["image_size"], hps["image_size"])).astype(np.uint8)).to(device)
+    noise = {}
+    for i in range(hps["depth"]):
+        size = hps["image_size"] // 2 ** (i + 1)
+        for j in range(hps["num_blocks"]):
+            noise[(i, j)] = torch.from_numpy(rng.randn(B, hps["z_size"], size, size).astype(np.float32)).to(dtype).to(device)
+    return params, x, noise
+
+
+def test_plumbing_against_oracle_primitives_cpu():
+    hps = dict(z_size=4, h_size=8, depth=2, num_blocks=2, kl_min=0.25, image_size=16)
+    params, x, noise = _setup(hps, 2, 3, torch.float64, "cpu")
+    # conv2d (stride 1) equals the oracle's weight-normed cross-correlation with an all-ones mask
+    h = torch.randn(2, 8, 8, 8, dtype=torch.float64)
+    got = elbo.conv2d(params, "IAF_0_0/up_conv3", h).numpy()
+    V, g, b = (params["IAF_0_0/up_conv3/" + k].numpy() for k in "Vgb")
+    w = O.tf_effective_weight(V, g, np.ones_like(V))
+    np.testing.assert_allclose(got, O.xcorr2d_same(h.numpy(), w) + b.reshape(1, -1, 1, 1), atol=1e-12)
+    # deconv2d is the adjoint of the SAME stride-2 conv with the same filter: <conv(a), c> == <a, deconv(c)>
+    pz = {"t/V": params["IAF_1_0/down_deconv2/V"], "t/g": torch.zeros(8, dtype=torch.float64), "t/b": torch.zeros(8, dtype=torch.float64)}
+    a = torch.randn(1, 8, 8, 8, dtype=torch.float64)
+    c = torch.randn(1, 12, 4, 4, dtype=torch.float64)
+    Vn = pz["t/V"] * torch.rsqrt((pz["t/V"] ** 2).sum(dim=(0, 1, 2), keepdim=True))
+    fwd = torch.nn.functional.conv2d(torch.nn.functional.pad(a, (0, 1, 0, 1)), Vn.permute(3, 2, 0, 1), stride=2)
+    assert abs(float((fwd * c).sum()) - float((a * elbo.deconv2d(pz, "t", c)).sum())) < 1e-9
+    out = elbo.forward(params, x, noise, OracleIAF(params, hps), hps)
+    assert np.isfinite(float(out["bits_per_dim"])) and out["kl_cost"].shape == (2,)
+    # free bits: kl_obj >= kl_cost can differ, and the objective uses the local batch mean (tf_train.py:77-83)
+    assert float(out["obj"]) != float((out["kl_cost"] - out["log_pxz"]).sum())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("hps,B", [
+    (dict(z_size=32, h_size=64, depth=2, num_blocks=2, kl_min=0.25, image_size=32), 4),   # fused tcgen05 path, two levels
+    (dict(z_size=32, h_size=160, depth=1, num_blocks=3, kl_min=0.1, image_size=32), 2),   # C3 shapes: layered tcgen05 path
+])
+def test_bits_per_dim_parity(hps, B):
+    pg, xg, ng = _setup(hps, B, 7, torch.float32, "cuda")
+    pc, xc, nc = _setup(hps, B, 7, torch.float64, "cpu")
+    got = elbo.forward(pg, xg, ng, elbo.CudaIAF(pg, hps), hps)
+    ref = elbo.forward(pc, xc, nc, OracleIAF(pc, hps), hps)
+    rel = abs(float(got["bits_per_dim"]) - float(ref["bits_per_dim"])) / abs(float(ref["bits_per_dim"]))
+    assert rel < 1e-4, (float(got["bits_per_dim"]), float(ref["bits_per_dim"]))
+    np.testing.assert_allclose(got["kl_cost"].cpu().numpy(), ref["kl_cost"].numpy(), rtol=2e-4, atol=1e-2)
+    np.testing.assert_allclose(float(got["obj"]), float(ref["obj"]), rtol=1e-4)
+
+
+def _dp_worker(rank, world, port, q):
+    import os
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    hps = dict(z_size=4, h_size=8, depth=1, num_blocks=2, kl_min=0.0, image_size=8)
+    params, x, noise = _setup(hps, 4, 11, torch.float64, "cpu")
+    bpd = elbo.sharded_bits_per_dim(params, x, noise, OracleIAF(params, hps), hps)
+    q.put((rank, float(bpd)))
+    dist.destroy_process_group()
+
+
+def test_sharded_elbo_equals_single_process_gloo_world2():
+    """C5's structure on CPU: 2 ranks, batch sharded, one all-reduce of the scalar (tf_train.py:126-142)."""
+    import os
+    import torch.multiprocessing as mp
+    hps = dict(z_size=4, h_size=8, depth=1, num_blocks=2, kl_min=0.0, image_size=8)
+    params, x, noise = _setup(hps, 4, 11, torch.float64, "cpu")
+    single = float(elbo.forward(params, x, noise, OracleIAF(params, hps), hps)["bits_per_dim"])
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    ps = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in ps)
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, v in res:
+        assert abs(v - single) < 1e-12 * max(1.0, abs(single))
