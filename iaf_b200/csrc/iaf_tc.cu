@@ -1172,7 +1172,30 @@ int iaf_tc_run(IafTcPlan* pl, const IafTcArgs* a, cudaStream_t stream, int* n_la
       q.stage_bytes = pl->ly_stage[j];
       q.n_bchunks = (pl->K[j] / 16) / LY_KC;
       { const char* tls = getenv("IAF_TL_STAGE"); q.tl_enable = tls ? (atoi(tls) == j) : (j == pl->n_stages - 1); }
-      lk<<<grid, LY_THREADS, pl->ly_smem[j], stream>>>(q);
+      // Optional: clusters of CTAs share the weight stream through TMA multicast (IAF_LY_CLUSTER=2|4).  Measured on
+      // B200 (C2b): 118.8 us without, 119.8 us with 2-CTA clusters, 199 us with 4 -- the stage is not limited by L2
+      // reads of the weights but by shared-memory operand bandwidth, and lock-stepping the ring across CTAs costs
+      // more than the saved L2 traffic; so the default stays 1.
+      int cs = 1;
+      {
+        const char* e = getenv("IAF_LY_CLUSTER");
+        const int want = e ? atoi(e) : 1;
+        const bool streams = q.n_bchunks > q.NB || q.in_mode;
+        if (streams && (2 * q.b_chunk_bytes) % (16 * want) == 0 && (want == 2 || want == 4) && grid % want == 0) cs = want;
+      }
+      q.cs = cs;
+      if (cs == 1) {
+        lk<<<grid, LY_THREADS, pl->ly_smem[j], stream>>>(q);
+      } else {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(LY_THREADS); cfg.dynamicSmemBytes = pl->ly_smem[j]; cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        if (cudaLaunchKernelEx(&cfg, lk, q) != cudaSuccess) return IAF_ERR_CUDA;
+      }
     }
     if (n_launches) *n_launches = pl->n_stages;
     return cudaGetLastError() == cudaSuccess ? IAF_OK : IAF_ERR_CUDA;

@@ -30,6 +30,32 @@ enum { LB_ACC_FULL = 0, LB_ACC_EMPTY = 2, LB_BFULL = 4, LB_BEMPTY = 4 + LY_MAX_N
        LB_AEMPTY = 6 + 2 * LY_MAX_NB + LY_MAX_KS,    // + K-step: the MMAs of that chunk pair are done
        LB_COUNT = 6 + 2 * LY_MAX_NB + 2 * LY_MAX_KS };
 
+// ---- thread-block-cluster helpers: the CTAs of a cluster stream the SAME weight chunks, so each loads 1/CS of a
+// chunk and TMA-multicasts it into every member's ring stage (L2 is read once per cluster instead of once per CTA)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_g2s_mcast(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+      : "memory");
+}
+// MMA-completion arrive on the same barrier of every CTA in the mask
+__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+
 struct IafLyParams {
   IafTcParams t;               // geometry, pointers, slot decoding (t.st[0] describes THIS stage)
   const __nv_bfloat16* a_hi;   // input operand image (in_mode 1)
@@ -46,6 +72,7 @@ struct IafLyParams {
   int b_chunk_bytes;           // bytes of one ring slot half (hi or lo): LY_KC * 2 * N * 16
   int n_bchunks;               // weight chunks per tile
   int tl_enable;               // timeline builds only: this launch flushes its events
+  int cs;                      // cluster size (1, 2 or 4): CTAs sharing the weight stream by TMA multicast
 };
 
 template <bool PADW, int MODE, int NLT, int THW>
@@ -62,7 +89,14 @@ __global__ void __launch_bounds__(LY_THREADS, 1) iaf_ly_kernel(const __grid_cons
   const int nchunk = St.cin >> 3;
   const int a_plane = p.WIN * 16;          // bytes per chunk plane of the A window
   const int a_lo_off = nchunk * a_plane;
-  const int n_my = (p.NT - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // tiles of this CTA
+  // tiles of this CTA: u = blockIdx.x + i * gridDim.x.  All CTAs of a cluster run the same number of iterations (the
+  // weight ring is shared); iterations whose tile index is past the end are "virtual": they consume the weight
+  // stream but load, compute and store nothing real.
+  const int cs = q.cs;
+  const int crank = cs > 1 ? (int)cluster_ctarank() : 0;
+  const int cfirst = (int)blockIdx.x - crank;  // first CTA of my cluster
+  const int n_my = (p.NT - cfirst + (int)gridDim.x - 1) / (int)gridDim.x;
+  const uint16_t cmask = (uint16_t)((1u << cs) - 1u);
   const int acc_cols = St.N;
   const bool resident = q.n_bchunks <= q.NB;
 
@@ -80,7 +114,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) iaf_ly_kernel(const __grid_cons
       }
       for (int i = 0; i < LY_MAX_NB; ++i) {
         mbar_init(&bars[LB_BFULL + i], 1);
-        mbar_init(&bars[LB_BEMPTY + i], 1);
+        mbar_init(&bars[LB_BEMPTY + i], (uint32_t)q.cs);  // every member of the cluster releases the stage
       }
       fence_barrier_init();
     }
@@ -96,6 +130,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) iaf_ly_kernel(const __grid_cons
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (cs > 1) cluster_sync_all();  // every member's barriers are initialised before any remote signal can arrive
   const uint32_t tmem_base = s_tmem;
 
   if (warp == LY_TMA_WARP) {
@@ -113,22 +148,34 @@ __global__ void __launch_bounds__(LY_THREADS, 1) iaf_ly_kernel(const __grid_cons
           if (use >= 1) mbar_wait(&bars[LB_BEMPTY + stg], (uint32_t)((use - 1) & 1));
           uint8_t* dst = smem + q.sm_b + stg * q.stage_bytes;
           const size_t bo = (size_t)c * q.b_chunk_bytes;
+          const bool real = u < p.NT;
           if (q.in_mode) {
             // one ring stage = A chunk pair (hi c0, hi c1, lo c0, lo c1) + the weight chunk (hi, lo) of K-step c
-            mbar_expect_tx(&bars[LB_BFULL + stg], (uint32_t)(4 * a_plane + 2 * q.b_chunk_bytes));
+            mbar_expect_tx(&bars[LB_BFULL + stg], (uint32_t)((real ? 4 * a_plane : 0) + 2 * q.b_chunk_bytes));
+            if (real) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const size_t go = ((size_t)(2 * c + h) * q.S_pad + (size_t)u * TC_TILE) * 8;
-              bulk_g2s(dst + h * a_plane, q.a_hi + go, (uint32_t)a_plane, &bars[LB_BFULL + stg]);
-              bulk_g2s(dst + (2 + h) * a_plane, q.a_lo + go, (uint32_t)a_plane, &bars[LB_BFULL + stg]);
+              for (int h = 0; h < 2; ++h) {
+                const size_t go = ((size_t)(2 * c + h) * q.S_pad + (size_t)u * TC_TILE) * 8;
+                bulk_g2s(dst + h * a_plane, q.a_hi + go, (uint32_t)a_plane, &bars[LB_BFULL + stg]);
+                bulk_g2s(dst + (2 + h) * a_plane, q.a_lo + go, (uint32_t)a_plane, &bars[LB_BFULL + stg]);
+              }
             }
             dst += 4 * a_plane;
           } else {
             mbar_expect_tx(&bars[LB_BFULL + stg], (uint32_t)(2 * q.b_chunk_bytes));
           }
-          bulk_g2s(dst, reinterpret_cast<const uint8_t*>(St.whi) + bo, (uint32_t)q.b_chunk_bytes, &bars[LB_BFULL + stg]);
-          bulk_g2s(dst + q.b_chunk_bytes, reinterpret_cast<const uint8_t*>(St.wlo) + bo, (uint32_t)q.b_chunk_bytes,
-                   &bars[LB_BFULL + stg]);
+          if (cs == 1) {
+            bulk_g2s(dst, reinterpret_cast<const uint8_t*>(St.whi) + bo, (uint32_t)q.b_chunk_bytes, &bars[LB_BFULL + stg]);
+            bulk_g2s(dst + q.b_chunk_bytes, reinterpret_cast<const uint8_t*>(St.wlo) + bo, (uint32_t)q.b_chunk_bytes,
+                     &bars[LB_BFULL + stg]);
+          } else {
+            // my 1/cs slice of the stage's [hi | lo] weight bytes, multicast into every member's stage
+            const int slice = 2 * q.b_chunk_bytes / cs;
+            const int so = crank * slice;
+            const uint8_t* src = so < q.b_chunk_bytes ? reinterpret_cast<const uint8_t*>(St.whi) + bo + so
+                                                      : reinterpret_cast<const uint8_t*>(St.wlo) + bo + (so - q.b_chunk_bytes);
+            bulk_g2s_mcast(dst + so, src, (uint32_t)slice, &bars[LB_BFULL + stg], cmask);
+          }
           ++gchunk;
         }
       }
@@ -182,7 +229,10 @@ __global__ void __launch_bounds__(LY_THREADS, 1) iaf_ly_kernel(const __grid_cons
           LY_TAP(3u, sh3, 1u)
           LY_TAP(4u, sh4, 1u)
 #undef LY_TAP
-          if (!res) umma_commit(&bars[LB_BEMPTY + stg]);
+          if (!res) {
+            if (cs == 1) umma_commit(&bars[LB_BEMPTY + stg]);
+            else umma_commit_mcast(&bars[LB_BEMPTY + stg], cmask);
+          }
           if (!q.in_mode) umma_commit(&bars[LB_AEMPTY + c]);
           if (c == q.n_bchunks - 1) {
             umma_commit(&bars[LB_ACC_FULL + b]);
@@ -321,10 +371,12 @@ float v[16];
               v[e] = o * validf;
             }
           }
+          if (u < p.NT) {
 #pragma unroll
-          for (int hch = 0; hch < 2; ++hch) {
-            const size_t go = (((size_t)((c0 >> 3) + hch)) * q.S_pad + (size_t)u * TC_TILE + sl) * 8;
-            split_store8(v + 8 * hch, reinterpret_cast<uint8_t*>(q.o_hi + go), reinterpret_cast<uint8_t*>(q.o_lo + go));
+            for (int hch = 0; hch < 2; ++hch) {
+              const size_t go = (((size_t)((c0 >> 3) + hch)) * q.S_pad + (size_t)u * TC_TILE + sl) * 8;
+              split_store8(v + 8 * hch, reinterpret_cast<uint8_t*>(q.o_hi + go), reinterpret_cast<uint8_t*>(q.o_lo + go));
+            }
           }
         }
         if (!waited) mbar_wait(&bars[LB_ACC_FULL + b], (uint32_t)(use & 1));
@@ -477,6 +529,7 @@ float v[16];
 
   tc_fence_before();
   __syncthreads();
+  if (cs > 1) cluster_sync_all();  // no member leaves while peers may still multicast into it or signal its barriers
   if (q.tl_enable) { TL_FLUSH }
   if (warp == LY_MMA_WARP) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
