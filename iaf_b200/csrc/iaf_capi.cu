@@ -314,11 +314,12 @@ static int run(iaf_plan* pl, int mode, const float* z, const float* ctx, const f
   if (!pl->packed) return IAF_ERR_NOT_PACKED;
   if (B <= 0) return IAF_ERR_BAD_ARG;
   const iaf_desc_t& d = pl->d;
-  if (pl->path == IAF_PATH_TC && mode != IAF_MODE_MULTICONV && iaf_tc_mode_supported(pl->tc, mode)) {
+  if (pl->path == IAF_PATH_TC && iaf_tc_mode_supported(pl->tc, mode)) {
     IafTcArgs a;
     memset(&a, 0, sizeof(a));
     a.mode = mode; a.z = z; a.ctx = ctx; a.post_mean = post_mean; a.post_logsd = post_logsd;
     a.prior_mean = prior_mean; a.prior_logsd = prior_logsd; a.z_out = z_out; a.elem_out = elem_out;
+    if (mode == IAF_MODE_MULTICONV) { a.z_out = m_out; a.elem_out = s_out; }  // raw heads travel in the same slots
     a.bc_out = bc_out; a.persample_out = persample_out; a.B = B;
     int nl = 0;
     int st = iaf_tc_run(pl->tc, &a, stream, &nl);

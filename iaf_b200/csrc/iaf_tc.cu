@@ -615,6 +615,11 @@ float v[16];
                   if (byH) { m += tb[3 * St.N + c0 + e]; sv += tb[3 * St.N + c0 + 8 + e]; }
                   if (byH || bxW) { m += tb[4 * St.N + c0 + e]; sv += tb[4 * St.N + c0 + 8 + e]; }
                 }
+                if (MODE == IAF_MODE_MULTICONV) {  // the un-fused operator: raw heads (ar.py:405-411 / layers.py:166)
+                  p.z_out[gi + (size_t)e * HW] = m;
+                  p.elem[gi + (size_t)e * HW] = sv;
+                  continue;
+                }
                 const float arw_mean = p.scale * m, arw_logsd = p.scale * sv;  // models.py:282-285
                 const size_t ge = gi + (size_t)e * HW;
                 float z0 = zv[e];
@@ -841,6 +846,10 @@ struct IafTcPlan {
 typedef void (*TcKernel)(const IafTcParams);
 template <int THW>
 static TcKernel tc_kernel_pick(bool padw, int mode, bool elu) {
+  if (mode == IAF_MODE_MULTICONV) {
+    if (padw) return elu ? iaf_tc_kernel<true, IAF_MODE_MULTICONV, IAF_NL_ELU, THW> : iaf_tc_kernel<true, IAF_MODE_MULTICONV, -1, THW>;
+    return elu ? iaf_tc_kernel<false, IAF_MODE_MULTICONV, IAF_NL_ELU, THW> : iaf_tc_kernel<false, IAF_MODE_MULTICONV, -1, THW>;
+  }
   if (mode == IAF_MODE_STEP) {
     if (padw) return elu ? iaf_tc_kernel<true, IAF_MODE_STEP, IAF_NL_ELU, THW> : iaf_tc_kernel<true, IAF_MODE_STEP, -1, THW>;
     return elu ? iaf_tc_kernel<false, IAF_MODE_STEP, IAF_NL_ELU, THW> : iaf_tc_kernel<false, IAF_MODE_STEP, -1, THW>;
@@ -856,6 +865,10 @@ static TcKernel tc_kernel_for(bool padw, int mode, bool elu, int hw) {
 typedef void (*LyKernel)(const IafLyParams);
 template <int THW>
 static LyKernel ly_kernel_pick(bool padw, int mode, bool elu) {
+  if (mode == IAF_MODE_MULTICONV) {
+    if (padw) return elu ? iaf_ly_kernel<true, IAF_MODE_MULTICONV, IAF_NL_ELU, THW> : iaf_ly_kernel<true, IAF_MODE_MULTICONV, -1, THW>;
+    return elu ? iaf_ly_kernel<false, IAF_MODE_MULTICONV, IAF_NL_ELU, THW> : iaf_ly_kernel<false, IAF_MODE_MULTICONV, -1, THW>;
+  }
   if (mode == IAF_MODE_STEP) {
     if (padw) return elu ? iaf_ly_kernel<true, IAF_MODE_STEP, IAF_NL_ELU, THW> : iaf_ly_kernel<true, IAF_MODE_STEP, -1, THW>;
     return elu ? iaf_ly_kernel<false, IAF_MODE_STEP, IAF_NL_ELU, THW> : iaf_ly_kernel<false, IAF_MODE_STEP, -1, THW>;
@@ -1001,14 +1014,15 @@ int iaf_tc_plan_create(IafTcPlan** out, const iaf_desc_t* d) {
   }
   size_t ly_max = 0;
   for (int j = 0; j < pl->n_stages; ++j) ly_max = std::max(ly_max, pl->ly_smem[j]);
-  for (int a = 0; a < 8; ++a) {
+  for (int a = 0; a < 12; ++a) {
     cudaError_t e;
+    const int md = (a >> 2) == 0 ? IAF_MODE_MULTICONV : ((a >> 2) == 1 ? IAF_MODE_STEP : IAF_MODE_LAYER);
     if (pl->layered)
-      e = cudaFuncSetAttribute(ly_kernel_for(a & 1, (a & 2) ? IAF_MODE_LAYER : IAF_MODE_STEP, a & 4, d->H * d->W),
-                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ly_max);
+      e = cudaFuncSetAttribute(ly_kernel_for(a & 1, md, a & 2, d->H * d->W), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)ly_max);
     else
-      e = cudaFuncSetAttribute(tc_kernel_for(a & 1, (a & 2) ? IAF_MODE_LAYER : IAF_MODE_STEP, a & 4, d->H * d->W),
-                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem);
+      e = cudaFuncSetAttribute(tc_kernel_for(a & 1, md, a & 2, d->H * d->W), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)pl->smem);
     if (e != cudaSuccess) {
       iaf_tc_plan_destroy(pl);
       return IAF_ERR_CUDA;
@@ -1086,7 +1100,9 @@ extern "C" void iaf_tc_timeline_dump(void) {
 }
 #endif
 
-bool iaf_tc_mode_supported(const IafTcPlan* pl, int mode) { return mode == IAF_MODE_STEP || (mode == IAF_MODE_LAYER && pl->layer_ok); }
+bool iaf_tc_mode_supported(const IafTcPlan* pl, int mode) {
+  return mode == IAF_MODE_STEP || mode == IAF_MODE_MULTICONV || (mode == IAF_MODE_LAYER && pl->layer_ok);
+}
 bool iaf_tc_is_layered(const IafTcPlan* pl) { return pl->layered; }
 
 int iaf_tc_run(IafTcPlan* pl, const IafTcArgs* a, cudaStream_t stream, int* n_launches) {

@@ -430,7 +430,12 @@ float v[16];
                 if (byH) { m += tb[3 * St.N + c0 + e]; sv += tb[3 * St.N + c0 + 8 + e]; }
                 if (byH || bxW) { m += tb[4 * St.N + c0 + e]; sv += tb[4 * St.N + c0 + 8 + e]; }
               }
-              const float arw_mean = p.scale * m, arw_logsd = p.scale * sv;  // models.py:282-285
+              if (MODE == IAF_MODE_MULTICONV) {  // the un-fused operator: raw heads (ar.py:405-411 / layers.py:166)
+                  p.z_out[gi + (size_t)e * HW] = m;
+                  p.elem[gi + (size_t)e * HW] = sv;
+                  continue;
+                }
+                const float arw_mean = p.scale * m, arw_logsd = p.scale * sv;  // models.py:282-285
               const size_t ge = gi + (size_t)e * HW;
               float z0 = zv[e];
               float eps = 0.f, pls = 0.f;

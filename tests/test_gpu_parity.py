@@ -55,10 +55,11 @@ def test_multiconv_against_reference_fixtures(ci):
     name, variant, B, n_z, hidden, H, W, nl = MULTICONV_CASES[ci]
     g = np.load(os.path.join(G, "multiconv.npz"))
     hid, heads, z, ctx = case_inputs(variant, B, n_z, hidden, H, W, seed=ci)
-    op = make_op(variant, n_z, hidden, nl, "simt", hid, heads)
-    m, s = op.multiconv(torch.from_numpy(z).cuda(), torch.from_numpy(ctx).cuda())
-    assert relerr(m, g[name + "_m"]) < 2e-5
-    assert relerr(s, g[name + "_s"]) < 2e-5
+    for path in (paths_for(variant, n_z, hidden, H, W) if hidden else ["simt"]):
+        op = make_op(variant, n_z, hidden, nl, path, hid, heads)
+        m, s = op.multiconv(torch.from_numpy(z).cuda(), torch.from_numpy(ctx).cuda())
+        assert relerr(m, g[name + "_m"]) < 2e-5, path
+        assert relerr(s, g[name + "_s"]) < 2e-5, path
 
 
 STEP_CASES = [
