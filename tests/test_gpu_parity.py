@@ -269,3 +269,46 @@ def test_step_host_entry_matches_device_entry():
     for zi, o in outs:
         ref = op.step(zi.cuda(), torch.from_numpy(ctx).cuda())
         assert torch.equal(o[0], ref[0].cpu()) and torch.equal(o[1], ref[1].cpu()) and torch.equal(o[2], ref[2].cpu())
+
+
+@pytest.mark.parametrize("variant,B,hidden,H,W", [
+    ("tf", 300, [64], 16, 16),         # 678 tiles over 148 CTAs: runs of 4 and 5 tiles
+    ("theano", 97, [64], 16, 16),      # odd batch, point-reflected orientation, pad channel
+    ("theano", 515, [64], 4, 4),       # 5+ samples per 128-slot tile
+    ("tf", 37, [160, 160], 16, 16),    # layer-at-a-time kernels, fewer tiles than SMs
+    ("theano", 150, [160, 160], 8, 8), # layered, several samples per tile
+])
+def test_tensor_core_paths_agree_with_fp32_path_at_odd_batches(variant, B, hidden, H, W):
+    """Cross-check of the two independent CUDA implementations (exact-fp32 SIMT vs tcgen05) on batch sizes that
+    exercise uneven tile runs, partial last tiles and tiles spanning many samples."""
+    n_z = 32
+    hid, heads = O.make_params(variant, n_z, hidden, [n_z, n_z], seed=5)
+    z, ctx = O.make_inputs(B, n_z, hidden[0], H, W, seed=6)
+    zc, cc = torch.from_numpy(z).cuda(), torch.from_numpy(ctx).cuda()
+    a = make_op(variant, n_z, hidden, "elu", "simt", hid, heads).step(zc, cc)
+    b = make_op(variant, n_z, hidden, "elu", "tc", hid, heads).step(zc, cc)
+    for x, y in zip(a, b):
+        assert relerr(y, x.double().cpu().numpy()) < 5e-5
+
+
+def test_full_size_properties_theano_c1():
+    """C1 (Theano numerics, hidden [64]) at B=256: determinism, AR direction (raster order: a perturbation only
+    reaches LATER raster positions), logdet consistency."""
+    variant, B, n_z, hidden, H, W = "theano", 256, 32, [64], 16, 16
+    hid, heads = O.make_params(variant, n_z, hidden, [n_z, n_z], seed=1)
+    z, ctx = O.make_inputs(B, n_z, hidden[0], H, W, seed=0)
+    zc, cc = torch.from_numpy(z).cuda(), torch.from_numpy(ctx).cuda()
+    for path in paths_for(variant, n_z, hidden, H, W):
+        op = make_op(variant, n_z, hidden, "elu", path, hid, heads)
+        z1, logsd, logdet = op.step(zc, cc)
+        assert relerr(logdet, -logsd.double().sum(dim=(1, 2, 3)).cpu().numpy()) < 1e-5
+        z1c, _, logdetc = op.step(zc, cc)
+        assert torch.equal(z1c, z1) and torch.equal(logdetc, logdet)
+        y0, x0 = 7, 9
+        zp = zc.clone()
+        zp[:, :, y0, x0] += 0.5
+        z1p, _, _ = op.step(zp, cc)
+        p0 = y0 * W + x0
+        flat, flatp = z1.reshape(B, n_z, -1), z1p.reshape(B, n_z, -1)
+        assert torch.equal(flat[:, :, :p0], flatp[:, :, :p0])            # earlier raster positions untouched
+        assert not torch.equal(flat[:, :, p0 + 1:], flatp[:, :, p0 + 1:])
