@@ -152,3 +152,32 @@ def test_sharded_elbo_reduction_gloo_world2():
     assert [(r[1], r[2]) for r in res] == [(0, 5), (5, 10)]
     for r in res:
         assert r[3] == [45.0, 10.0]
+
+
+def test_weight_containers_roundtrip(tmp_path):
+    """The reference's Theano weight container (graphy/ndict.py:209-236) and the name maps of both front-ends."""
+    from iaf_b200 import weights
+    hid, heads = O.make_params("theano", 4, [8], [4, 4], seed=9)
+    w = {}
+    for i, l in enumerate(hid):
+        for k in "wsb":
+            w["0_1_posterior_conv1_%d_%s" % (i, k)] = l[k]
+    for i, l in enumerate(heads):
+        for k in "wsb":
+            w["0_1_posterior_conv1_out_%d_%s" % (i, k)] = l[k]
+    w["logsd_x"] = np.zeros((), np.float32)
+    f = str(tmp_path / "weights.ndict.tar.gz")
+    weights.np_savez(w, f)
+    back = weights.np_loadz(f)
+    assert sorted(back) == sorted(w) and all(np.array_equal(back[k], w[k]) for k in w)
+    layers = weights.theano_layers(back, "0_1_posterior_conv1", 1, device="cpu")
+    assert len(layers) == 3 and tuple(layers[0][0].shape) == (8, 5, 3, 3) and tuple(layers[2][1].shape) == (4,)
+    assert np.array_equal(layers[1][0].numpy(), heads[0]["w"])
+    hid, heads = O.make_params("tf", 4, [8, 8], [4, 4], seed=9)
+    v = {}
+    for n, l in zip(["layer_0", "layer_1", "layer_out_0", "layer_out_1"], hid + heads):
+        for k in "Vgb":
+            v["model/IAF_0_3/ar_multiconv2d/%s/%s" % (n, k)] = l[k]
+    layers = weights.tf_layers(v, "model/IAF_0_3/ar_multiconv2d", device="cpu")
+    assert len(layers) == 4 and tuple(layers[1][0].shape) == (3, 3, 8, 8)
+    assert np.array_equal(layers[3][2].numpy(), heads[1]["b"])
