@@ -39,10 +39,13 @@
 
 #include "iaf_tc.h"
 
-#define TC_WORKERS 16
+#ifndef TC_WORKERS
+#define TC_WORKERS 16  // worker warps (multiple of 4: TMEM lane quadrants)
+#endif
 #define TC_WTHREADS (TC_WORKERS * 32)
-#define TC_THREADS (TC_WTHREADS + 32)
+#define TC_THREADS (TC_WTHREADS + 64)
 #define TC_CTRL_WARP TC_WORKERS
+#define TC_RED_WARP (TC_WORKERS + 1)
 #define TC_TILE 128
 #ifdef IAF_TC_TIMELINE
 #define TC_SMEM_LIMIT (227 * 1024 - 2048 - 6144)  // room for the static event buffers
@@ -52,7 +55,7 @@
 #define TC_NGROUPS 1   // 1: all 16 worker warps run every phase together; 2: two ping-pong groups by tile parity
 #define TC_GWARPS (TC_WORKERS / TC_NGROUPS)
 #define TC_GTHREADS (TC_GWARPS * 32)
-#define TC_ZITEMS (TC_NGROUPS == 1 ? 2 : 3)  // z-window (slot, chunk) items per loader thread
+#define TC_ZITEMS (TC_GTHREADS >= 512 ? 2 : (TC_GTHREADS >= 256 ? 3 : 5))  // z-window (slot, chunk) items per loader thread
 
 enum {
   BAR_W = 0, BAR_ZFULL = 1, BAR_ZEMPTY = 2,
@@ -60,8 +63,9 @@ enum {
   BAR_ACC_EMPTY = 13,  // + 2*j + b
   BAR_H_FULL = 23,     // + 2*j + b   (ring written by stage j)
   BAR_H_EMPTY = 31,    // + 2*j + b
-  BAR_PART = 40,       // + tile parity
-  BAR_COUNT = 42
+  BAR_PART = 40,       // + tile parity: the workers' partial sums of a heads tile are deposited
+  BAR_PART_EMPTY = 42, // + tile parity: the reducer warp has consumed them
+  BAR_COUNT = 44
 };
 
 struct IafTcStage {
@@ -314,6 +318,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
       }
       mbar_init(&bars[BAR_PART], TC_GWARPS);
       mbar_init(&bars[BAR_PART + 1], TC_GWARPS);
+      mbar_init(&bars[BAR_PART_EMPTY], 1);
+      mbar_init(&bars[BAR_PART_EMPTY + 1], 1);
       fence_barrier_init();
       uint32_t total = 0;
       for (int j = 0; j < nst; ++j) total += 2u * (uint32_t)p.st[j].w_bytes;
@@ -326,7 +332,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
         }
       }
     }
-  } else {
+  } else if (warp < TC_WORKERS) {
     // bias (+ pad-channel) tables -> smem: [5][N] per stage (row 0 bias, rows 1..4 padw)
     for (int j = 0; j < nst; ++j) {
       float* tb = reinterpret_cast<float*>(smem + p.st[j].sm_bias);
@@ -406,7 +412,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
       }
     }
     __syncwarp();
-  } else {
+  } else if (warp < TC_WORKERS) {
     // =====================================================================================
     // worker warps: z loader + epilogues.  TMEM lane quadrant = warp % 4; the 4 warps of a
     // quadrant split the accumulator columns in groups of 16.
@@ -580,6 +586,8 @@ float v[16];
           const int n_last = min(p.B - 1, fast_div(tile_s0 + TC_TILE - 1, p.SPS, p.mg_sps));
           const int ns = (tile_s0 < p.S) ? (n_last - n_first + 1) : 0;
           const int pb = k & 1;  // partial-sum buffer
+          if (MODE == IAF_MODE_LAYER && (p.persample_out || p.bc_out) && k >= 2)
+            mbar_wait(&bars[BAR_PART_EMPTY + pb], (uint32_t)(((k >> 1) - 1) & 1));
           bool waited = false;
           for (int g = cg; g < ngroups; g += CGS) {
             const int c0 = g * 16;
@@ -672,6 +680,7 @@ float v[16];
           if (p.persample_out || p.bc_out) {
             constexpr bool LAY = (MODE == IAF_MODE_LAYER);
             if (!LAY) {
+              if (k >= 2) mbar_wait(&bars[BAR_PART_EMPTY + pb], (uint32_t)(((k >> 1) - 1) & 1));
               for (int nl_ = 0; nl_ < ns; ++nl_) {
                 float x = (si.valid && si.n == n_first + nl_) ? red[0] : 0.f;
 #pragma unroll
@@ -681,7 +690,27 @@ float v[16];
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars[BAR_PART + pb]);
-            if (gwarp == 0) {
+          }
+        }
+      }
+    }
+  }
+
+  if (warp == TC_RED_WARP && (p.persample_out || p.bc_out) && MODE != IAF_MODE_MULTICONV) {
+    // =====================================================================================
+    // reducer warp: folds the workers' per-tile partial sums into the per-tile partials in global memory and, for
+    // samples whose last tile this is, into the outputs -- off the workers' critical path
+    // =====================================================================================
+    float* s_part = reinterpret_cast<float*>(smem + p.sm_part);
+    constexpr bool LAY = (MODE == IAF_MODE_LAYER);
+    for (int k = 0; k < nt; ++k) {
+      const int u = t0 + k;
+      const int pb = k & 1;
+      const int tile_s0 = u * TC_TILE;
+      const int n_first = fast_div(tile_s0, p.SPS, p.mg_sps);
+      const int n_last = min(p.B - 1, fast_div(tile_s0 + TC_TILE - 1, p.SPS, p.mg_sps));
+      const int ns = (tile_s0 < p.S) ? (n_last - n_first + 1) : 0;
+      {
               mbar_wait(&bars[BAR_PART + pb], (uint32_t)((k >> 1) & 1));
               const int cred = LAY ? p.C : 1;
               for (int i = lane; i < ns * cred; i += 32) {
@@ -690,7 +719,7 @@ float v[16];
                   const int nl_ = i / p.C, c = i - nl_ * p.C;
                   for (int qq = 0; qq < 4; ++qq) tot += s_part[((pb * 4 + qq) * p.MAXS + nl_) * p.C + c];
                 } else {
-                  for (int w = 0; w < TC_GWARPS; ++w) tot += s_part[(pb * TC_GWARPS + w) * p.MAXS + i];
+                  for (int w = 0; w < TC_WORKERS; ++w) tot += s_part[(pb * TC_WORKERS + w) * p.MAXS + i];
                 }
                 p.tilepart[((size_t)u * p.MAXS) * cred + i] = tot;
                 __threadfence();
@@ -718,10 +747,9 @@ float v[16];
                   if (p.persample_out) p.persample_out[n] = LAY ? cost : -cost;  // logdet = -sum(arw_logsd)
                 }
               }
-            }
-          }
-        }
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[BAR_PART_EMPTY + pb]);
     }
   }
 

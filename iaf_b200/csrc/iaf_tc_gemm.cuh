@@ -20,7 +20,8 @@
 #define LY_WTHREADS (LY_WORKERS * 32)
 #define LY_MMA_WARP LY_WORKERS
 #define LY_TMA_WARP (LY_WORKERS + 1)
-#define LY_THREADS (LY_WTHREADS + 64)
+#define LY_RED_WARP (LY_WORKERS + 2)
+#define LY_THREADS (LY_WTHREADS + 96)
 #define LY_KC 5        // K-steps (of 16) per weight chunk
 #define LY_MAX_NB 6
 
@@ -28,7 +29,8 @@
 enum { LB_ACC_FULL = 0, LB_ACC_EMPTY = 2, LB_BFULL = 4, LB_BEMPTY = 4 + LY_MAX_NB, LB_PART = 4 + 2 * LY_MAX_NB,
        LB_AFULL = 6 + 2 * LY_MAX_NB,                 // + K-step: chunk pair (2ks, 2ks+1) of the A window has landed
        LB_AEMPTY = 6 + 2 * LY_MAX_NB + LY_MAX_KS,    // + K-step: the MMAs of that chunk pair are done
-       LB_COUNT = 6 + 2 * LY_MAX_NB + 2 * LY_MAX_KS };
+       LB_PART_EMPTY = 6 + 2 * LY_MAX_NB + 2 * LY_MAX_KS,  // + tile parity: the reducer warp has consumed the partials
+       LB_COUNT = 8 + 2 * LY_MAX_NB + 2 * LY_MAX_KS };
 
 // ---- thread-block-cluster helpers: the CTAs of a cluster stream the SAME weight chunks, so each loads 1/CS of a
 // chunk and TMA-multicasts it into every member's ring stage (L2 is read once per cluster instead of once per CTA)
@@ -111,6 +113,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) iaf_ly_kernel(const __grid_cons
         mbar_init(&bars[LB_ACC_FULL + i], 1);
         mbar_init(&bars[LB_ACC_EMPTY + i], LY_WORKERS);
         mbar_init(&bars[LB_PART + i], LY_WORKERS);
+        mbar_init(&bars[LB_PART_EMPTY + i], 1);
       }
       for (int i = 0; i < LY_MAX_NB; ++i) {
         mbar_init(&bars[LB_BFULL + i], 1);
@@ -243,7 +246,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) iaf_ly_kernel(const __grid_cons
         if (!res) ++gchunk;
       }
     }
-  } else {
+  } else if (warp < LY_WORKERS) {
     // ===================== workers: (first stage) z -> operand window; epilogues =====================
     const int qd = warp & 3, cg = warp >> 2;
     constexpr int CGS = LY_WORKERS / 4;
@@ -395,6 +398,8 @@ float v[16];
         const int n_last = min(p.B - 1, fast_div(tile_s0 + TC_TILE - 1, p.SPS, p.mg_sps));
         const int ns = (tile_s0 < p.S) ? (n_last - n_first + 1) : 0;
         const int pb = i & 1;
+        if (MODE == IAF_MODE_LAYER && (p.persample_out || p.bc_out) && i >= 2)
+          mbar_wait(&bars[LB_PART_EMPTY + pb], (uint32_t)(((i >> 1) - 1) & 1));
         bool waited = false;
         for (int g = cg; g < ngroups; g += CGS) {
           const int c0 = g * 16;
@@ -480,6 +485,7 @@ float v[16];
         if (p.persample_out || p.bc_out) {
           constexpr bool LAY = (MODE == IAF_MODE_LAYER);
           if (!LAY) {
+            if (i >= 2) mbar_wait(&bars[LB_PART_EMPTY + pb], (uint32_t)(((i >> 1) - 1) & 1));
             for (int nl_ = 0; nl_ < ns; ++nl_) {
               float x = (si.valid && si.n == n_first + nl_) ? red[0] : 0.f;
 #pragma unroll
@@ -489,7 +495,23 @@ float v[16];
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars[LB_PART + pb]);
-          if (warp == 0) {
+        }
+      }
+    }
+  }
+
+  if (warp == LY_RED_WARP && q.is_heads && (p.persample_out || p.bc_out) && MODE != IAF_MODE_MULTICONV) {
+    // ===================== reducer warp: per-tile partials -> per-sample outputs, off the workers' critical path ==========
+    float* s_part = reinterpret_cast<float*>(smem + q.sm_part);
+    constexpr bool LAY = (MODE == IAF_MODE_LAYER);
+    for (int i = 0; i < n_my; ++i) {
+      const int u = (int)blockIdx.x + i * (int)gridDim.x;
+      const int pb = i & 1;
+      const int tile_s0 = u * TC_TILE;
+      const int n_first = fast_div(tile_s0, p.SPS, p.mg_sps);
+      const int n_last = min(p.B - 1, fast_div(tile_s0 + TC_TILE - 1, p.SPS, p.mg_sps));
+      const int ns = (tile_s0 < p.S) ? (n_last - n_first + 1) : 0;
+      {
             mbar_wait(&bars[LB_PART + pb], (uint32_t)((i >> 1) & 1));
             const int cred = LAY ? p.C : 1;
             for (int k_ = lane; k_ < ns * cred; k_ += 32) {
@@ -526,9 +548,9 @@ float v[16];
                 if (p.persample_out) p.persample_out[n] = LAY ? cost : -cost;
               }
             }
-          }
-        }
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[LB_PART_EMPTY + pb]);
     }
   }
 
