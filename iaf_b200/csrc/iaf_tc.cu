@@ -81,6 +81,8 @@ struct IafTcStage {
   int sm_bias;               // smem byte offset of the fp32 bias (+ padw) table: [5][N]
   int tmem_col;
   int dbl;                   // accumulator double-buffered in TMEM
+  int merged;                // hi*[hi|lo] issued as ONE N' = 2N MMA (A is fetched once for both): accumulator spans 2N cols
+  int acc_cols;              // N or 2N
 };
 
 struct IafTcParams {
@@ -325,10 +327,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
       for (int j = 0; j < nst; ++j) total += 2u * (uint32_t)p.st[j].w_bytes;
       mbar_expect_tx(&bars[BAR_W], total);
       for (int j = 0; j < nst; ++j) {
-        for (int off = 0; off < p.st[j].w_bytes; off += 32768) {
-          const uint32_t n = (uint32_t)min(32768, p.st[j].w_bytes - off);
+        for (int off = 0; off < 2 * p.st[j].w_bytes; off += 32768) {
+          const uint32_t n = (uint32_t)min(32768, 2 * p.st[j].w_bytes - off);
           bulk_g2s(smem + p.st[j].sm_whi + off, reinterpret_cast<const uint8_t*>(p.st[j].whi) + off, n, &bars[BAR_W]);
-          bulk_g2s(smem + p.st[j].sm_wlo + off, reinterpret_cast<const uint8_t*>(p.st[j].wlo) + off, n, &bars[BAR_W]);
         }
       }
     }
@@ -376,17 +377,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
           tc_fence_after();
           if (lane == 0) TL(0, 100 + j, k);
 
-          const uint32_t d_tmem = tmem_base + (uint32_t)(St.tmem_col + b * St.N);
-          const uint32_t idesc = umma_idesc(St.N);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(St.tmem_col + b * St.acc_cols);
+          const uint32_t idesc = umma_idesc(St.N), idesc2 = umma_idesc(2 * St.N);
+          const int merged = St.merged;
           const uint32_t a_plane = (uint32_t)St.in_slots * 16u;
           const uint32_t a_base = smem_u32(smem + St.sm_in) + (uint32_t)((j == 0 ? 0 : (k & 1) * TC_TILE)) * 16u;
           const uint32_t nchunk = (uint32_t)(St.cin >> 3);
-          const uint32_t b_plane = (uint32_t)St.N * 16u;
+          const uint32_t b_plane = (uint32_t)(2 * St.N) * 16u;  // weight image plane: N hi rows then N lo rows
           // descriptor low words; every step below is a plain add in units of 16 B
           const uint32_t ah0 = umma_desc_lo(a_base, a_plane);
           const uint32_t al0 = umma_desc_lo(a_base + nchunk * a_plane, a_plane);
           uint32_t bh = umma_desc_lo(smem_u32(smem + St.sm_whi), b_plane);
-          uint32_t bl = umma_desc_lo(smem_u32(smem + St.sm_wlo), b_plane);
+          uint32_t bl = umma_desc_lo(smem_u32(smem + St.sm_whi) + (uint32_t)St.N * 16u, b_plane);
           const uint32_t a_kstep = (2u * a_plane) >> 4, b_kstep = (2u * b_plane) >> 4;
           const int nks = St.cin >> 4;
           if (elect_one_sync()) {
@@ -395,10 +397,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
           for (int tp = 0; tp < IAF_NTAPS; ++tp) {
             uint32_t ah = ah0 + (uint32_t)shifts[tp], al = al0 + (uint32_t)shifts[tp];
             for (int ks = 0; ks < nks; ++ks) {
-              umma_bf16(d_tmem, mk_desc(al), mk_desc(bh), idesc, acc);  // lo * hi
+              if (merged) {
+                // hi * [hi | lo] as one N' = 2N instruction (A fetched once for both), then lo * hi into the hi half
+                umma_bf16(d_tmem, mk_desc(ah), mk_desc(bh), idesc2, acc);
+                umma_bf16(d_tmem, mk_desc(al), mk_desc(bh), idesc, 1u);
+              } else {
+                umma_bf16(d_tmem, mk_desc(al), mk_desc(bh), idesc, acc);  // lo * hi
+                umma_bf16(d_tmem, mk_desc(ah), mk_desc(bl), idesc, 1u);   // hi * lo
+                umma_bf16(d_tmem, mk_desc(ah), mk_desc(bh), idesc, 1u);   // hi * hi
+              }
               acc = 1;
-              umma_bf16(d_tmem, mk_desc(ah), mk_desc(bl), idesc, acc);  // hi * lo
-              umma_bf16(d_tmem, mk_desc(ah), mk_desc(bh), idesc, acc);  // hi * hi
               ah += a_kstep; al += a_kstep; bh += b_kstep; bl += b_kstep;
             }
           }
@@ -490,7 +498,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
         const SlotInfo si = decode_slot(p, u * TC_TILE + sl, HW);
         const bool bx0 = (si.x == 0), bxW = (si.x == p.W - 1), byH = (si.y == p.H - 1);
         const float* tb = reinterpret_cast<const float*>(smem + St.sm_bias);
-        const uint32_t t_acc = t_lane + (uint32_t)(St.tmem_col + b * St.N);
+        const uint32_t t_acc = t_lane + (uint32_t)(St.tmem_col + b * St.acc_cols);
         const int ngroups = St.N >> 4;
 
         if (!last) {
@@ -523,7 +531,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
             uint32_t r[16];
             tmem_ld16(t_acc + (uint32_t)c0, r);
             tmem_ld_wait();
-float v[16];
+            if (St.merged) {  // hi*lo partial products sit in columns [N, 2N)
+              uint32_t r2[16];
+              tmem_ld16(t_acc + (uint32_t)(St.N + c0), r2);
+              tmem_ld_wait();
+#pragma unroll
+              for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) + __uint_as_float(r2[e]));
+            }
+            float v[16];
             {
               // branch-free: bias rows come in as 16-byte vectors, the pad-channel terms (conv.py:77-83: the pad
               // channel is 1 where a tap falls outside the image) are 0/1-weighted FMAs, and an invalid slot
@@ -608,6 +623,13 @@ float v[16];
             uint32_t r[16];
             tmem_ld16(t_acc + (uint32_t)c0, r);
             tmem_ld_wait();
+            if (St.merged) {
+              uint32_t r2[16];
+              tmem_ld16(t_acc + (uint32_t)(St.N + c0), r2);
+              tmem_ld_wait();
+#pragma unroll
+              for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) + __uint_as_float(r2[e]));
+            }
             if (MODE == IAF_MODE_LAYER) {
 #pragma unroll
               for (int i = 0; i < NRED; ++i) red[i] = 0.f;
@@ -829,10 +851,17 @@ __global__ void __launch_bounds__(128) iaf_tc_pack_kernel(const __grid_constant_
       v *= factor;
       // K order: fused kernel [tap][ci]; layer-at-a-time kernel [ci / 16][tap][ci % 16]
       const int k = p.korder ? (((ci >> 4) * IAF_NTAPS + t) * 16 + (ci & 15)) : (t * L.cin + ci);
-      const size_t o = ((size_t)(k >> 3) * L.N + col) * 8 + (k & 7);
       const __nv_bfloat16 h = __float2bfloat16_rn(v);
-      L.whi[o] = h;
-      L.wlo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
+      const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+      if (p.korder) {  // layered kernel: separate hi / lo images [K/8][N][8]
+        const size_t o = ((size_t)(k >> 3) * L.N + col) * 8 + (k & 7);
+        L.whi[o] = h;
+        L.wlo[o] = l;
+      } else {         // fused kernel: one image [K/8][2N][8], per K chunk the N hi rows then the N lo rows
+        const size_t o = ((size_t)(k >> 3) * 2 * L.N + col) * 8 + (k & 7);
+        L.whi[o] = h;
+        L.whi[o + (size_t)L.N * 8] = l;
+      }
     } else {
       const int t = e - n_real + 1;
       L.padw_out[(size_t)(t - 1) * L.N + col] = tc_raw_weight(L, p.variant, t, L.cin, co) * factor;
@@ -853,7 +882,7 @@ struct IafTcPlan {
   float* bias[IAF_MAX_STAGES];
   float* padw[IAF_MAX_STAGES];
   int sm_whi[IAF_MAX_STAGES], sm_wlo[IAF_MAX_STAGES], sm_in[IAF_MAX_STAGES], in_slots[IAF_MAX_STAGES];
-  int sm_bias[IAF_MAX_STAGES], tmem_col[IAF_MAX_STAGES], dbl[IAF_MAX_STAGES];
+  int sm_bias[IAF_MAX_STAGES], tmem_col[IAF_MAX_STAGES], dbl[IAF_MAX_STAGES], merged[IAF_MAX_STAGES], acc_cols[IAF_MAX_STAGES];
   int MIR, WIN, RING, MAXS, sm_part, tmem_cols;
   bool layer_ok;             // the per-(sample,channel) scratch of the fused-layer mode fits
   // layer-at-a-time mode (hidden widths that do not fit the fused kernel's on-chip rings)
@@ -951,14 +980,22 @@ static bool tc_layout(const iaf_desc_t* d, IafTcPlan* pl) {
   const int part_layer = 2 * 4 * q->MAXS * d->n_z * 4;
   q->layer_ok = (off + std::max(part_step, part_layer)) <= TC_SMEM_LIMIT;
   off += q->layer_ok ? std::max(part_step, part_layer) : part_step;
-  // TMEM: double-buffer as many accumulators as fit in 512 columns, the heads first
+  // TMEM (512 columns): double-buffer every accumulator if possible, then spend what is left on the merged
+  // hi*[hi|lo] form (accumulator spans 2N columns, one MMA and one A fetch fewer per K step), the heads first
   int cols = 0;
-  for (int j = 0; j < nst; ++j) { q->dbl[j] = 0; cols += q->N[j]; }
+  for (int j = 0; j < nst; ++j) { q->dbl[j] = 0; q->merged[j] = 0; q->acc_cols[j] = q->N[j]; cols += q->N[j]; }
   if (cols > 512) return false;
   for (int j = nst - 1; j >= 0; --j)
     if (cols + q->N[j] <= 512) { q->dbl[j] = 1; cols += q->N[j]; }
+  // (A/B on one B200, C2a: merged 30.6 us vs 31.3 us without: the heads' MMAs drop 3.3K -> 2.7K cycles per tile, most of
+  //  which the second TMEM read in the epilogues gives back; IAF_TC_MERGED=0 switches it off)
+  const char* mg = getenv("IAF_TC_MERGED");
+  for (int j = nst - 1; j >= 0 && !(mg && mg[0] == '0'); --j) {
+    const int extra = q->N[j] * (1 + q->dbl[j]);
+    if (2 * q->N[j] <= 256 && cols + extra <= 512) { q->merged[j] = 1; q->acc_cols[j] = 2 * q->N[j]; cols += extra; }
+  }
   int col = 0;
-  for (int j = 0; j < nst; ++j) { q->tmem_col[j] = col; col += q->N[j] * (1 + q->dbl[j]); }
+  for (int j = 0; j < nst; ++j) { q->tmem_col[j] = col; col += q->acc_cols[j] * (1 + q->dbl[j]); }
   int tc = 32;
   while (tc < col) tc *= 2;
   q->tmem_cols = tc;
@@ -1033,7 +1070,7 @@ int iaf_tc_plan_create(IafTcPlan** out, const iaf_desc_t* d) {
   pl->num_sms = prop.multiProcessorCount;
   for (int j = 0; j < pl->n_stages; ++j) {
     const size_t wb = (size_t)pl->K[j] * pl->N[j] * 2;
-    if (cudaMalloc(&pl->whi[j], wb) != cudaSuccess || cudaMalloc(&pl->wlo[j], wb) != cudaSuccess ||
+    if (cudaMalloc(&pl->whi[j], 2 * wb) != cudaSuccess || cudaMalloc(&pl->wlo[j], wb) != cudaSuccess ||
         cudaMalloc(&pl->bias[j], sizeof(float) * pl->N[j]) != cudaSuccess ||
         cudaMalloc(&pl->padw[j], sizeof(float) * 4 * pl->N[j]) != cudaSuccess) {
       iaf_tc_plan_destroy(pl);
@@ -1086,7 +1123,7 @@ int iaf_tc_pack(IafTcPlan* pl, const float* const* w, const float* const* scale,
   int max_cout = 0;
   for (int j = 0; j < pl->n_stages; ++j) {
     const size_t wb = (size_t)pl->K[j] * pl->N[j] * 2;
-    if (cudaMemsetAsync(pl->whi[j], 0, wb, stream) != cudaSuccess) return IAF_ERR_CUDA;
+    if (cudaMemsetAsync(pl->whi[j], 0, 2 * wb, stream) != cudaSuccess) return IAF_ERR_CUDA;
     if (cudaMemsetAsync(pl->wlo[j], 0, wb, stream) != cudaSuccess) return IAF_ERR_CUDA;
     if (cudaMemsetAsync(pl->padw[j], 0, sizeof(float) * 4 * pl->N[j], stream) != cudaSuccess) return IAF_ERR_CUDA;
   }
@@ -1180,7 +1217,7 @@ int iaf_tc_run(IafTcPlan* pl, const IafTcArgs* a, cudaStream_t stream, int* n_la
     S_.w_bytes = pl->K[j] * pl->N[j] * 2;
     S_.sm_whi = pl->sm_whi[j]; S_.sm_wlo = pl->sm_wlo[j]; S_.sm_in = pl->sm_in[j];
     S_.in_slots = pl->in_slots[j]; S_.sm_bias = pl->sm_bias[j];
-    S_.tmem_col = pl->tmem_col[j]; S_.dbl = pl->dbl[j];
+    S_.tmem_col = pl->tmem_col[j]; S_.dbl = pl->dbl[j]; S_.merged = pl->merged[j]; S_.acc_cols = pl->acc_cols[j];
   }
   p.B = B; p.C = d.n_z; p.H = d.H; p.W = d.W; p.Wp = d.W + 1; p.SPS = SPS; p.HW = d.H * d.W;
   p.S = S; p.NT = NT;
