@@ -52,7 +52,9 @@
 #else
 #define TC_SMEM_LIMIT (227 * 1024 - 2048)
 #endif
+#ifndef TC_NGROUPS
 #define TC_NGROUPS 1   // 1: all 16 worker warps run every phase together; 2: two ping-pong groups by tile parity
+#endif
 #define TC_GWARPS (TC_WORKERS / TC_NGROUPS)
 #define TC_GTHREADS (TC_GWARPS * 32)
 #define TC_ZITEMS (TC_GTHREADS >= 512 ? 2 : (TC_GTHREADS >= 256 ? 3 : 5))  // z-window (slot, chunk) items per loader thread
@@ -741,7 +743,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
                   const int nl_ = i / p.C, c = i - nl_ * p.C;
                   for (int qq = 0; qq < 4; ++qq) tot += s_part[((pb * 4 + qq) * p.MAXS + nl_) * p.C + c];
                 } else {
-                  for (int w = 0; w < TC_WORKERS; ++w) tot += s_part[(pb * TC_WORKERS + w) * p.MAXS + i];
+                  for (int w = 0; w < TC_GWARPS; ++w) tot += s_part[(pb * TC_GWARPS + w) * p.MAXS + i];
                 }
                 p.tilepart[((size_t)u * p.MAXS) * cred + i] = tot;
                 __threadfence();
