@@ -43,6 +43,12 @@ WORKLOADS = {
     # name: (variant, n_z, hidden, H, W, B, roofline bound)
     "c2a": ("tf", 32, [64], 16, 16, 256, "hbm"),
     "c2b": ("tf", 32, [160, 160], 16, 16, 256, "tensor"),
+    # per-step shapes of the other BASELINE configs (parity-test cases; benched for the record, not the headline)
+    "c1": ("theano", 32, [64], 16, 16, 16, "hbm"),              # README example, batch 16, level 0
+    "c1_l1": ("theano", 32, [64], 8, 8, 16, "hbm"),             # ... level 1
+    "c1_l2": ("theano", 32, [64], 4, 4, 16, "hbm"),             # ... level 2
+    "c3": ("tf", 32, [160, 160], 16, 16, 32, "tensor"),         # tf_train.py default per-GPU batch
+    "c4_l1": ("theano", 32, [160, 160], 8, 8, 16, "tensor"),    # Table-3 config, second level
 }
 METRIC = "IAF latents/sec (z',logdet) @ n_z=32,16x16,bs256"
 UNIT = "latent elements/s"
@@ -126,8 +132,11 @@ def make_workload(name, device, nsets, seed=0):
     for i in range(len(hidden) + 2):
         cin = sizes[min(i, len(hidden))]
         cout = hidden[i] if i < len(hidden) else n_z
-        V = 0.05 * torch.randn((3, 3, cin, cout), generator=g)
+        shape = (3, 3, cin, cout) if variant == "tf" else (cout, cin + 1, 3, 3)
+        V = 0.05 * torch.randn(shape, generator=g)
         gg = torch.rand((cout,), generator=g) - 0.5
+        if variant == "theano":
+            gg = gg / 3.0
         b = 0.1 * torch.randn((cout,), generator=g)
         layers.append((V, gg, b))
     op = IAFOperator(variant, n_z, hidden, [n_z, n_z], nl="elu", path="auto")
@@ -152,8 +161,9 @@ def cpu_port_runner(name, layers_cpu, sample_B, threads):
     g = torch.Generator().manual_seed(0)
     z = torch.randn((sample_B, n_z, H, W), generator=g)
     ctx = 0.1 * torch.randn((sample_B, hidden[0], H, W), generator=g)
-    hid = [dict(V=l[0], g=l[1], b=l[2]) for l in layers_cpu[:len(hidden)]]
-    heads = [dict(V=l[0], g=l[1], b=l[2]) for l in layers_cpu[len(hidden):]]
+    keys = ("V", "g", "b") if variant == "tf" else ("w", "s", "b")
+    hid = [dict(zip(keys, l)) for l in layers_cpu[:len(hidden)]]
+    heads = [dict(zip(keys, l)) for l in layers_cpu[len(hidden):]]
 
     def fn():
         with torch.no_grad():
@@ -231,7 +241,7 @@ def main():
     ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2a", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c2a", choices=sorted(WORKLOADS))  # c2a = the headline
     ap.add_argument("--no-graph", action="store_true", help="K direct launches instead of one CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

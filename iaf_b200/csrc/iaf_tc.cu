@@ -306,6 +306,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
   const int s_max = nt + 2 * nst - 3;  // last period: heads on tile nt-1 at s = nt-1 + 2(nst-1)
 
   // ---- one-time setup ----
+  // Programmatic dependent launch: let the next grid in the stream start launching while this one runs (its CTAs
+  // take the SMs our short-run CTAs free early), and do our own TMEM allocation / barrier init before waiting for
+  // the previous grid; nothing that another kernel may have written is touched before griddepcontrol.wait.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (warp == TC_CTRL_WARP) {
     tmem_alloc(&s_tmem, (uint32_t)p.tmem_cols);
     if (lane == 0) {
@@ -325,6 +329,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
       mbar_init(&bars[BAR_PART_EMPTY], 1);
       mbar_init(&bars[BAR_PART_EMPTY + 1], 1);
       fence_barrier_init();
+      asm volatile("griddepcontrol.wait;" ::: "memory");
       uint32_t total = 0;
       for (int j = 0; j < nst; ++j) total += 2u * (uint32_t)p.st[j].w_bytes;
       mbar_expect_tx(&bars[BAR_W], total);
@@ -336,6 +341,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
       }
     }
   } else if (warp < TC_WORKERS) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     // bias (+ pad-channel) tables -> smem: [5][N] per stage (row 0 bias, rows 1..4 padw)
     for (int j = 0; j < nst; ++j) {
       float* tb = reinterpret_cast<float*>(smem + p.st[j].sm_bias);
@@ -348,6 +354,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
       }
     }
   }
+  if (warp == TC_RED_WARP) asm volatile("griddepcontrol.wait;" ::: "memory");
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1267,16 +1274,17 @@ int iaf_tc_run(IafTcPlan* pl, const IafTcArgs* a, cudaStream_t stream, int* n_la
         if (streams && (2 * q.b_chunk_bytes) % (16 * want) == 0 && (want == 2 || want == 4) && grid % want == 0) cs = want;
       }
       q.cs = cs;
-      if (cs == 1) {
-        lk<<<grid, LY_THREADS, pl->ly_smem[j], stream>>>(q);
-      } else {
+      {
+        const char* pe = getenv("IAF_PDL");
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
         cfg.gridDim = dim3(grid); cfg.blockDim = dim3(LY_THREADS); cfg.dynamicSmemBytes = pl->ly_smem[j]; cfg.stream = stream;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
+        cudaLaunchAttribute at[2];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = (pe && pe[0] == '0') ? 0 : 1;
+        at[1].id = cudaLaunchAttributeClusterDimension;
+        at[1].val.clusterDim.x = cs; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = cs > 1 ? 2 : 1;
         if (cudaLaunchKernelEx(&cfg, lk, q) != cudaSuccess) return IAF_ERR_CUDA;
       }
     }
@@ -1284,7 +1292,17 @@ int iaf_tc_run(IafTcPlan* pl, const IafTcArgs* a, cudaStream_t stream, int* n_la
     return cudaGetLastError() == cudaSuccess ? IAF_OK : IAF_ERR_CUDA;
   }
   TcKernel k = tc_kernel_for(d.variant == IAF_VARIANT_THEANO, a->mode, d.nl == IAF_NL_ELU, d.H * d.W);
-  k<<<grid, TC_THREADS, pl->smem, stream>>>(p);
+  {
+    const char* e = getenv("IAF_PDL");
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = pl->smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = (e && e[0] == '0') ? 0 : 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, k, p) != cudaSuccess) return IAF_ERR_CUDA;
+  }
   if (n_launches) *n_launches = 1;
   return cudaGetLastError() == cudaSuccess ? IAF_OK : IAF_ERR_CUDA;
 }

@@ -102,6 +102,8 @@ __global__ void __launch_bounds__(LY_THREADS, 1) iaf_ly_kernel(const __grid_cons
   const int acc_cols = St.N;
   const bool resident = q.n_bchunks <= q.NB;
 
+  // programmatic dependent launch (see iaf_tc_kernel): everything up to the barrier init overlaps the previous grid
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (warp == LY_MMA_WARP) {
     tmem_alloc(&s_tmem, (uint32_t)p.tmem_cols);
     if (lane == 0) {
@@ -122,6 +124,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) iaf_ly_kernel(const __grid_cons
       fence_barrier_init();
     }
   } else if (warp < LY_WORKERS) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     float* tb = reinterpret_cast<float*>(smem + q.sm_bias);
     for (int i = tid; i < 5 * St.N; i += LY_WTHREADS) {
       float v = 0.f;
@@ -130,6 +133,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) iaf_ly_kernel(const __grid_cons
       tb[i] = v;
     }
   }
+  if (warp >= LY_WORKERS) asm volatile("griddepcontrol.wait;" ::: "memory");  // producer / MMA / reducer warps
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
