@@ -123,9 +123,16 @@ class ClockSampler(object):
                 "samples": len(timed), "window": window}
 
 
-def make_workload(name, device, nsets, seed=0):
-    from iaf_b200 import IAFOperator
-    variant, n_z, hidden, H, W, B, bound = WORKLOADS[name]
+def workload_string(name):
+    variant, n_z, hidden, H, W, B, _ = WORKLOADS[name]
+    return "%s: single IAF step, n_z=%d hidden=%s %dx%d batch %d per GPU, %s-variant numerics" % (
+        name, n_z, hidden, H, W, B, variant)
+
+
+def make_layers(name, seed=0):
+    """Seeded synthetic (direction, gain, bias) per conv in the variant's own layout: TF V[3,3,Cin,Cout], g, b
+    (layers.py:53-55); Theano w[Cout,Cin+1,3,3], s, b (ar.py:288-296; its gain is exp(3 s))."""
+    variant, n_z, hidden = WORKLOADS[name][:3]
     g = torch.Generator().manual_seed(seed + 1)
     sizes = [n_z] + hidden
     layers = []
@@ -139,6 +146,13 @@ def make_workload(name, device, nsets, seed=0):
             gg = gg / 3.0
         b = 0.1 * torch.randn((cout,), generator=g)
         layers.append((V, gg, b))
+    return layers
+
+
+def make_workload(name, device, nsets, seed=0):
+    from iaf_b200 import IAFOperator
+    variant, n_z, hidden, H, W, B, bound = WORKLOADS[name]
+    layers = make_layers(name, seed)
     op = IAFOperator(variant, n_z, hidden, [n_z, n_z], nl="elu", path="auto")
     op.set_weights([tuple(t.to(device) for t in l) for l in layers])
     g = torch.Generator().manual_seed(seed)
@@ -204,14 +218,7 @@ def run_reference(args, rank, world):
     name = args.workload
     variant, n_z, hidden, H, W, B, bound = WORKLOADS[name]
     threads = os.cpu_count() or 1
-    g = torch.Generator().manual_seed(1)
-    sizes = [n_z] + hidden
-    layers = []
-    for i in range(len(hidden) + 2):
-        cin = sizes[min(i, len(hidden))]
-        cout = hidden[i] if i < len(hidden) else n_z
-        layers.append((0.05 * torch.randn((3, 3, cin, cout), generator=g), torch.rand((cout,), generator=g) - 0.5,
-                       0.1 * torch.randn((cout,), generator=g)))
+    layers = make_layers(name)
     # bounded sample: the full 256-sample batch per step, at most 50 steps
     sample_B = B
     fn, elems = cpu_port_runner(name, layers, sample_B, threads)
@@ -224,8 +231,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": t * 1e3 * (B / sample_B), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s: single IAF step, n_z=%d hidden=%s %dx%d batch %d, TF-variant numerics" %
-                   (name, n_z, hidden, H, W, B), "sample": "%d of %d samples per step, %d steps" % (sample_B, B, steps)},
+        "config": {"workload": workload_string(name), "sample": "%d of %d samples per step, %d steps" % (sample_B, B, steps)},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": "%d of the %d samples per step, %d steps, torch-CPU fp32 port of the "
                                    "reference path (Theano/TF originals cannot run here)" % (sample_B, B, steps)},
@@ -436,8 +442,7 @@ def main():
         "ms_per_step": t_total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 (tc path: bf16x3 split operands, f32 accumulate)" if op.path_used(H, W, device) == "tc" else "f32",
         "data": "synthetic",
-        "config": {"workload": "%s: single IAF step, n_z=%d hidden=%s %dx%d batch %d per GPU, TF-variant numerics" %
-                   (name, n_z, hidden, H, W, B), "global_batch": B * world, "parallelism": "dp%d" % world,
+        "config": {"workload": workload_string(name), "global_batch": B * world, "parallelism": "dp%d" % world,
                    "path": op.path_used(H, W, device), "launch": launch_mode, "kernels_per_step": launches_per_step,
                    "l2": "rotating %d input/output sets (%.0f MB > 126 MB L2)" % (nsets, nsets * alg_bytes_unit / 2 ** 20),
                    "collective": "one all-reduce of the scalar sum(logdet) per timed region" if world > 1 else "none",
