@@ -14,6 +14,12 @@ import numpy as np
 import torch
 
 
+def _as_f32(a, device):
+    if torch.is_tensor(a):
+        return a.detach().to(torch.float32).contiguous().to(device)
+    return torch.as_tensor(np.ascontiguousarray(np.asarray(a, dtype=np.float32))).to(device)
+
+
 def np_loadz(filename):
     """Read a graphy ``.ndict.tar.gz`` (graphy/ndict.py:228-236) -> dict name -> ndarray."""
     with tarfile.open(filename, "r:gz") as tar:
@@ -39,12 +45,12 @@ def np_savez(d, filename):
 def theano_layers(w, name, n_hidden, n_heads=2, device="cuda"):
     """(w, s, b) triples, hidden layers first, for ``multiconv2d(name, ...)`` parameters in ``w``."""
     names = ["%s_%d" % (name, i) for i in range(n_hidden)] + ["%s_out_%d" % (name, k) for k in range(n_heads)]
-    t = lambda a: torch.as_tensor(np.ascontiguousarray(np.asarray(a, dtype=np.float32))).to(device)
+    t = lambda a: _as_f32(a, device)
     return [(t(w[n + "_w"]), t(w[n + "_s"]), t(w[n + "_b"])) for n in names]
 
 
 def tf_layers(variables, scope, n_hidden=2, n_heads=2, device="cuda"):
     """(V, g, b) triples for ``ar_multiconv2d`` under ``scope`` (e.g. ``model/IAF_0_3/ar_multiconv2d``)."""
     names = ["layer_%d" % i for i in range(n_hidden)] + ["layer_out_%d" % k for k in range(n_heads)]
-    t = lambda a: torch.as_tensor(np.ascontiguousarray(np.asarray(a, dtype=np.float32))).to(device)
+    t = lambda a: _as_f32(a, device)
     return [tuple(t(variables["%s/%s/%s" % (scope, n, k)]) for k in "Vgb") for n in names]

@@ -1,5 +1,6 @@
-"""Oracle-side `iaf_layer` for iaf_b200.elbo.forward (TEST INFRASTRUCTURE ONLY): the stochastic-layer
-block of tf_train.py:56-85 evaluated with oracle/iaf_oracle.py in float64 on the CPU."""
+"""Oracle-side `iaf_layer` callables for iaf_b200.elbo.forward / iaf_b200.elbo_theano.forward (TEST INFRASTRUCTURE
+ONLY): the stochastic-layer block of tf_train.py:56-85 / models.py:273-298 evaluated with oracle/iaf_oracle.py in
+float64 on the CPU."""
 import numpy as np
 import torch
 
@@ -18,5 +19,25 @@ class OracleIAF(object):
         zero = np.zeros_like(f(eps))
         r = O.stochastic_layer_down("tf", f(eps), f(post_mean), f(post_logsd), zero, zero, f(prior_mean), f(prior_logsd),
                                     f(context), np.zeros_like(f(context)), hidden, heads, "elu", kl_min=0.0)
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(eps.dtype).to(eps.device)
+        return t(r["z"]), t(r["kl"].sum(axis=(2, 3))), t(r["kl_cost"])
+
+
+class OracleIAFTheano(object):
+    """Theano front-end (models.py:273-298): parameters ``{name}_posterior_conv1_{k}_{w,s,b}`` / ``..._out_{k}_...``."""
+
+    def __init__(self, w, hps):
+        self.w, self.hps = w, hps
+
+    def __call__(self, name, eps, post_mean, post_logsd, prior_mean, prior_logsd, context):
+        f = lambda t: t.detach().cpu().numpy().astype(np.float64)
+        pre = name + "_posterior_conv1_"
+        layer = lambda n: {k: f(self.w[pre + n + "_" + k]) for k in "wsb"}
+        hidden = [layer("%d" % k) for k in range(self.hps["depth_ar"])]
+        heads = [layer("out_0"), layer("out_1")]
+        zero = np.zeros_like(f(eps))
+        r = O.stochastic_layer_down("theano", f(eps), f(post_mean), f(post_logsd), zero, zero, f(prior_mean),
+                                    f(prior_logsd), f(context), np.zeros_like(f(context)), hidden, heads,
+                                    self.hps["nl"], kl_min=0.0)
         t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(eps.dtype).to(eps.device)
         return t(r["z"]), t(r["kl"].sum(axis=(2, 3))), t(r["kl_cost"])

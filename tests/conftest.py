@@ -24,3 +24,15 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(autouse=True)
+def _fp32_plumbing():
+    """The ELBO plumbing around the operator (stock torch convs) must be plain fp32 in the parity tests: cuDNN/cuBLAS
+    would otherwise be free to use TF32 (1e-3 relative) and that, not the operator, would set the bits/dim error."""
+    import torch
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
