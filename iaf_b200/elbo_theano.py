@@ -1,12 +1,15 @@
 """ELBO forward of the Theano front-end around the IAF operator:
 `cvae1.f_encode_decode` (models.py:435-497) with `cvae_layer.up` / `cvae_layer.down_q` (models.py:133-328) for
-``posterior='down_iaf2_nl'``, ``prior='diag'``, ``px='logistic'``, ``downsample_type='nn'`` (the README configs,
-train.py:55-75), restated in PyTorch so that bits/dim can be compared between the B200 operator and the oracle
+``posterior='down_iaf2_nl'`` (the README configs, train.py:55-75) and ``posterior='up_iaf2_nl'`` (the bottom-up
+placement of the same operator, models.py:169-178), ``prior='diag'``, ``px='logistic'``, ``downsample_type='nn'``,
+restated in PyTorch so that bits/dim can be compared between the B200 operator and the oracle
 operator on identical weights, inputs and noise.
 
-As in :mod:`iaf_b200.elbo`, only the stochastic-layer block (posterior sample -> IAF step -> KL) goes through the
-pluggable ``iaf_layer`` callable; the rest is plumbing on stock torch ops.  Parameters are a dict under the reference's
-Theano names (graphy/nodes/conv.py:156-173, ar.py:288-296): ``x_enc_{w,b,s}``, ``x_dec_{w,b,s}``, ``logsd_x``,
+As in :mod:`iaf_b200.elbo`, only the stochastic-layer block goes through a pluggable callable: for down_iaf2_nl the
+fused ``iaf_layer`` (posterior sample -> IAF step -> KL against the prior, all known in the top-down pass), for
+up_iaf2_nl the plain step ``iaf_layer.step(name, z, context) -> (z', arw_logsd)`` in the bottom-up pass (the prior is
+only known later, so the KL is assembled top-down from the stored sample and log q); the rest is plumbing on stock
+torch ops.  Parameters are a dict under the reference's Theano names (graphy/nodes/conv.py:156-173, ar.py:288-296): ``x_enc_{w,b,s}``, ``x_dec_{w,b,s}``, ``logsd_x``,
 ``h_top``, ``{i}_{j}_up_conv1_{ds}_*``, ``{i}_{j}_up_conv2_*``, ``{i}_{j}_down_conv1_*``, ``{i}_{j}_down_conv2_{ds}_*``,
 ``{i}_{j}_posterior_conv1_{k}_*`` and ``{i}_{j}_posterior_conv1_out_{k}_*``.
 """
@@ -70,14 +73,28 @@ def upsample_nn(x):
     return x.repeat_interleave(2, dim=2).repeat_interleave(2, dim=3)
 
 
-def layer_up(w, name, h_in, hps, downsample):
-    """cvae_layer.up for down_iaf2_nl (models.py:133-196): returns (output, (qz_mean, qz_logsd, up_context))."""
+def gaussian_logps(mean, logvar, x):
+    """graphy/nodes/rand.py:83."""
+    return -0.5 * (math.log(2 * math.pi) + logvar + (x - mean) ** 2 / torch.exp(logvar))
+
+
+def layer_up(w, name, h_in, hps, downsample, eps=None, iaf_layer=None):
+    """cvae_layer.up (models.py:133-196).  down_iaf2_nl: returns (output, (qz_mean, qz_logsd, up_context)).
+    up_iaf2_nl (models.py:169-178): the posterior sample is drawn and transformed HERE, with the context taken from
+    up_conv1's channels; returns (output, (z, logqs)) for the top-down pass."""
     nz, nh2, nl = hps["n_z"], hps["n_h2"], hps["nl"]
     ds = 2 if downsample else 1
     h = conv2d(w, "%s_up_conv1_%d" % (name, ds), nonlinearity(h_in, nl), downsample=ds)
     h_det, qz_mean, qz_logsd, up_context = torch.split(h, [nh2, nz, nz, nh2], dim=1)
     if downsample:
         h_in = downsample_nn(h_in)
+    if hps.get("posterior", "down_iaf2_nl") == "up_iaf2_nl":
+        z0 = qz_mean + torch.exp(qz_logsd) * eps                       # gaussian_diag(qz_mean, 2 qz_logsd).sample
+        logqs = gaussian_logps(qz_mean, 2 * qz_logsd, z0)
+        z, arw_logsd = iaf_layer.step(name, z0.contiguous(), up_context.contiguous())
+        logqs = logqs + arw_logsd                                      # models.py:174
+        hh = torch.cat([h_det, z], dim=1)
+        return h_in + 0.1 * conv2d(w, name + "_up_conv2", nonlinearity(hh, nl)), (z, logqs)
     return h_in + 0.1 * conv2d(w, name + "_up_conv2", nonlinearity(h_det, nl)), (qz_mean, qz_logsd, up_context)
 
 
@@ -86,6 +103,15 @@ def layer_down_q(w, name, h_in, up_state, eps, iaf_layer, hps, downsample):
     nz, nh2, nl = hps["n_z"], hps["n_h2"], hps["nl"]
     ds = 2 if downsample else 1
     h = conv2d(w, name + "_down_conv1", nonlinearity(h_in, nl))
+    if hps.get("posterior", "down_iaf2_nl") == "up_iaf2_nl":            # models.py:215-217, 287-290
+        h_det, pz_mean, pz_logsd = torch.split(h, [nh2, nz, nz], dim=1)
+        z, logqs = up_state
+        kl = logqs - gaussian_logps(pz_mean, 2 * pz_logsd, z)
+        hh = torch.cat([h_det, z], dim=1)
+        if downsample:
+            h_in = upsample_nn(h_in)
+        out = h_in + 0.1 * conv2d(w, "%s_down_conv2_%d" % (name, ds), nonlinearity(hh, nl), upsample=ds)
+        return out, kl.sum(dim=(2, 3)), kl.sum(dim=(1, 2, 3))
     # channel map: [h_det n_h2 | pz_mean n_z | pz_logsd n_z || rz_mean n_z | rz_logsd n_z | down_context n_h2]
     h_det, pz_mean, pz_logsd, rz_mean, rz_logsd, down_context = torch.split(h, [nh2, nz, nz, nz, nz, nh2], dim=1)
     qz_mean, qz_logsd, up_context = up_state
@@ -119,7 +145,7 @@ def forward(w, x_uint8, noise, iaf_layer, hps):
     ups = {}
     for i in range(len(depths)):
         for j in range(depths[i]):
-            h, ups[(i, j)] = layer_up(w, "%d_%d" % (i, j), h, hps, i > 0 and j == 0)
+            h, ups[(i, j)] = layer_up(w, "%d_%d" % (i, j), h, hps, i > 0 and j == 0, noise[(i, j)], iaf_layer)
     size = hps["image_size"] // 2 ** len(depths)
     h = w["h_top"].reshape(1, -1, 1, 1).expand(B, -1, size, size)
     results = {}
@@ -148,6 +174,7 @@ def make_params(hps, seed=0, dtype=np.float32):
     """Seeded synthetic parameters under the reference's Theano names and shapes (no checkpoint exists offline)."""
     rng = np.random.RandomState(seed)
     nz, nh1, nh2, depths = hps["n_z"], hps["n_h1"], hps["n_h2"], hps["depths"]
+    up_post = hps.get("posterior", "down_iaf2_nl") == "up_iaf2_nl"
     w = {}
 
     def conv(name, cin, cout, k, pad_channel=True):
@@ -164,8 +191,8 @@ def make_params(hps, seed=0, dtype=np.float32):
             n = "%d_%d" % (i, j)
             ds = 2 if (i > 0 and j == 0) else 1
             conv("%s_up_conv1_%d" % (n, ds), nh1, nh2 + 2 * nz + nh2, 3)
-            conv(n + "_up_conv2", nh2, nh1, 3)
-            conv(n + "_down_conv1", nh1, (nh2 + 2 * nz) + (2 * nz + nh2), 3)
+            conv(n + "_up_conv2", nh2 + nz if up_post else nh2, nh1, 3)                       # models.py:25,84
+            conv(n + "_down_conv1", nh1, (nh2 + 2 * nz) + (0 if up_post else 2 * nz + nh2), 3)  # models.py:27-28,86
             conv("%s_down_conv2_%d" % (n, ds), nh2 + nz, nh1 * ds * ds, 3)
             sizes = [nz] + hps["depth_ar"] * [nh2]
             for k in range(hps["depth_ar"]):
@@ -182,13 +209,22 @@ class CudaIAF(object):
         from .ops import IAFOperator
         self.w, self.hps, self.path, self.IAFOperator, self.ops = w, hps, path, IAFOperator, {}
 
-    def __call__(self, name, eps, post_mean, post_logsd, prior_mean, prior_logsd, context):
+    def _op(self, name, device):
         op = self.ops.get(name)
         if op is None:
             from .weights import theano_layers
             nz, nh2, dar = self.hps["n_z"], self.hps["n_h2"], self.hps["depth_ar"]
             op = self.IAFOperator("theano", nz, dar * [nh2], [nz, nz], nl=self.hps["nl"], path=self.path)   # models.py:92
-            op.set_weights(theano_layers(self.w, name + "_posterior_conv1", dar, device=eps.device))
+            op.set_weights(theano_layers(self.w, name + "_posterior_conv1", dar, device=device))
             self.ops[name] = op
-        z, _, kl_bc, kl_cost = op.layer(eps, post_mean, post_logsd, prior_mean, prior_logsd, context, want_kl=False)
+        return op
+
+    def __call__(self, name, eps, post_mean, post_logsd, prior_mean, prior_logsd, context):
+        z, _, kl_bc, kl_cost = self._op(name, eps.device).layer(eps, post_mean, post_logsd, prior_mean, prior_logsd,
+                                                                context, want_kl=False)
         return z, kl_bc, kl_cost
+
+    def step(self, name, z, context):
+        """up_iaf2_nl: the bare step (models.py:170-173) -> (z', arw_logsd)."""
+        z_new, arw_logsd, _ = self._op(name, z.device).step(z, context)
+        return z_new, arw_logsd

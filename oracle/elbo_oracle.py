@@ -41,3 +41,13 @@ class OracleIAFTheano(object):
                                     self.hps["nl"], kl_min=0.0)
         t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(eps.dtype).to(eps.device)
         return t(r["z"]), t(r["kl"].sum(axis=(2, 3))), t(r["kl_cost"])
+
+    def step(self, name, z, context):
+        """The bare step (models.py:170-173) for up_iaf2_nl -> (z', arw_logsd)."""
+        f = lambda t: t.detach().cpu().numpy().astype(np.float64)
+        pre = name + "_posterior_conv1_"
+        layer = lambda n: {k: f(self.w[pre + n + "_" + k]) for k in "wsb"}
+        hidden = [layer("%d" % k) for k in range(self.hps["depth_ar"])]
+        z_new, arw_logsd, _ = O.iaf_step("theano", f(z), f(context), hidden, [layer("out_0"), layer("out_1")], self.hps["nl"])
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(z.dtype).to(z.device)
+        return t(z_new), t(arw_logsd)

@@ -1,7 +1,7 @@
 """Golden vectors of the Theano front-end's stochastic layer, produced by EXECUTING the reference's own source:
 `cvae_layer(...).up` / `.down_q` (models.py:14-328) with `N.conv.conv2d` (graphy/nodes/conv.py:122-274),
 `N.ar.multiconv2d` (graphy/nodes/ar.py), `N.rand.gaussian_diag` (graphy/nodes/rand.py:78-87) and the
-nearest-neighbour resamplers (conv.py:36-49), for posterior='down_iaf2_nl', prior='diag'.
+nearest-neighbour resamplers (conv.py:36-49), for posterior='down_iaf2_nl' and 'up_iaf2_nl', prior='diag'.
 
 Run in the build container only (needs /root/reference):  python tests/golden/make_golden_theano_layer.py
 Writes tests/golden/cvae_layer_down.npz.  Same approach as make_golden.py: python2 -> python3 syntax shims, an
@@ -121,12 +121,13 @@ def main():
     models = load_theano_model(eps_queue)
     out = {}
     n_h1, n_h2, n_z, depth_ar, nl = 8, 8, 4, 1, "elu"
-    for name, downsample, H in (("0_1", False, 8), ("1_0", True, 8)):
-        np.random.seed(11 if downsample else 7)         # conv.py:156 / ar.py:288 draw the kernels from np.random
+    for name, posterior, downsample, H in (("0_1", "down_iaf2_nl", False, 8), ("1_0", "down_iaf2_nl", True, 8),
+                                           ("u0_1", "up_iaf2_nl", False, 8), ("u1_0", "up_iaf2_nl", True, 8)):
+        np.random.seed((11 if downsample else 7) + (100 if posterior[0] == "u" else 0))   # conv.py:156 / ar.py:288
         w = {}
-        layer = models["cvae_layer"](name, "diag", "down_iaf2_nl", n_h1, n_h2, n_z, depth_ar, downsample, nl, (3, 3),
+        layer = models["cvae_layer"](name, "diag", posterior, n_h1, n_h2, n_z, depth_ar, downsample, nl, (3, 3),
                                      False, "nn", w)
-        rng = np.random.RandomState(5 if downsample else 3)
+        rng = np.random.RandomState((5 if downsample else 3) + (100 if posterior[0] == "u" else 0))
         for k in sorted(w):                              # non-trivial scales and biases (the reference starts at 0)
             if k.endswith("_s"):
                 w[k] = _wrap(rng.uniform(-0.1, 0.1, size=w[k].shape))
@@ -137,9 +138,13 @@ def main():
         Hd = H // 2 if downsample else H                 # resolution of the stochastic layer and of the top-down input
         down_in = rng.randn(B, n_h1, Hd, Hd)
         eps = rng.randn(B, n_z, Hd, Hd)
-        eps_queue.append(rng.randn(B, n_z, Hd, Hd))      # qz[0] in up() draws a sample that down_iaf2_nl never uses
-        up_out = layer.up(_wrap(up_in), w)
-        eps_queue.append(eps)
+        if posterior == "up_iaf2_nl":
+            eps_queue.append(eps)                        # the posterior sample is drawn (and transformed) in up()
+            up_out = layer.up(_wrap(up_in), w)
+        else:
+            eps_queue.append(rng.randn(B, n_z, Hd, Hd))  # qz[0] in up() draws a sample that down_iaf2_nl never uses
+            up_out = layer.up(_wrap(up_in), w)
+            eps_queue.append(eps)
         down_out, kl = layer.down_q(_wrap(down_in), True, w)
         assert not eps_queue
         out.update({name + "/w/" + k: np.asarray(v) for k, v in w.items()})

@@ -13,16 +13,19 @@ from oracle.elbo_oracle import OracleIAFTheano
 GOLD = os.path.join(os.path.dirname(__file__), "golden", "cvae_layer_down.npz")
 
 
-@pytest.mark.parametrize("name", ["0_1", "1_0"])
+@pytest.mark.parametrize("name", ["0_1", "1_0", "u0_1", "u1_0"])
 def test_layer_matches_reference_models_py(name):
-    """cvae_layer.up / down_q (models.py:133-328) for down_iaf2_nl + diag prior, incl. conv.py's weight-normed convs
-    with pad channel, stride-2 / depth-to-space resampling, nearest-neighbour skip paths, and the IAF step."""
+    """cvae_layer.up / down_q (models.py:133-328) for down_iaf2_nl and up_iaf2_nl ("u" cases) + diag prior, incl.
+    conv.py's weight-normed convs with pad channel, stride-2 / depth-to-space resampling, nearest-neighbour skip paths,
+    and the IAF step."""
     g = np.load(GOLD)
     pre = name + "/"
     w = {k[len(pre) + 2:]: torch.from_numpy(g[k]) for k in g.files if k.startswith(pre + "w/")}
-    hps = dict(n_z=4, n_h1=8, n_h2=8, depths=[2, 2], depth_ar=1, nl="elu", kl_min=0.0, image_size=16)
+    hps = dict(n_z=4, n_h1=8, n_h2=8, depths=[2, 2], depth_ar=1, nl="elu", kl_min=0.0, image_size=16,
+               posterior="up_iaf2_nl" if name[0] == "u" else "down_iaf2_nl")
     ds = bool(g[pre + "downsample"])
-    up_out, up_state = ET.layer_up(w, name, torch.from_numpy(g[pre + "up_in"]), hps, ds)
+    up_out, up_state = ET.layer_up(w, name, torch.from_numpy(g[pre + "up_in"]), hps, ds, torch.from_numpy(g[pre + "eps"]),
+                                   OracleIAFTheano(w, hps))
     np.testing.assert_allclose(up_out.numpy(), g[pre + "up_out"], rtol=1e-10, atol=1e-10)
     out, kl_bc, kl_sum = ET.layer_down_q(w, name, torch.from_numpy(g[pre + "down_in"]), up_state,
                                          torch.from_numpy(g[pre + "eps"]), OracleIAFTheano(w, hps), hps, ds)
@@ -44,8 +47,9 @@ def _setup(hps, B, seed, dtype, device):
     return w, x, noise
 
 
-def test_forward_free_bits_and_shapes_cpu():
-    hps = dict(n_z=4, n_h1=8, n_h2=8, depths=[2, 2], depth_ar=1, nl="elu", kl_min=0.25, image_size=16)
+@pytest.mark.parametrize("posterior", ["down_iaf2_nl", "up_iaf2_nl"])
+def test_forward_free_bits_and_shapes_cpu(posterior):
+    hps = dict(n_z=4, n_h1=8, n_h2=8, depths=[2, 2], depth_ar=1, nl="elu", kl_min=0.25, image_size=16, posterior=posterior)
     w, x, noise = _setup(hps, 3, 5, torch.float64, "cpu")
     r = ET.forward(w, x, noise, OracleIAFTheano(w, hps), hps)
     assert r["cost"].shape == (3,) and np.isfinite(float(r["bits_per_dim"]))
@@ -66,6 +70,11 @@ def test_forward_free_bits_and_shapes_cpu():
     (dict(n_z=32, n_h1=160, n_h2=160, depths=[2, 2], depth_ar=2, nl="elu", kl_min=0.25, image_size=32), 2),
     # cvae1's default nonlinearity (models.py:384) runs on the exact-fp32 kernel's run-time switch as well
     (dict(n_z=32, n_h1=64, n_h2=64, depths=[1, 1], depth_ar=1, nl="softplus", kl_min=0.0, image_size=32), 2),
+    # the bottom-up placement (up_iaf2_nl, models.py:169-178): the bare step, KL assembled in the top-down pass
+    (dict(n_z=32, n_h1=64, n_h2=64, depths=[2, 2], depth_ar=1, nl="elu", kl_min=0.25, image_size=32,
+          posterior="up_iaf2_nl"), 4),
+    (dict(n_z=32, n_h1=160, n_h2=160, depths=[1, 1], depth_ar=2, nl="elu", kl_min=0.0, image_size=32,
+          posterior="up_iaf2_nl"), 2),
 ])
 def test_bits_per_dim_parity_theano(hps, B):
     wg, xg, ng = _setup(hps, B, 9, torch.float32, "cuda")

@@ -5,6 +5,7 @@ ELBO reduction works over gloo with world_size 2."""
 import ctypes as C
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -181,3 +182,23 @@ def test_weight_containers_roundtrip(tmp_path):
     layers = weights.tf_layers(v, "model/IAF_0_3/ar_multiconv2d", device="cpu")
     assert len(layers) == 4 and tuple(layers[1][0].shape) == (3, 3, 8, 8)
     assert np.array_equal(layers[3][2].numpy(), heads[1]["b"])
+
+
+def test_bench_reference_arm_line_schema():
+    """`bench.py --impl reference` (the CPU port of the reference path) prints ONE JSON line with the contract's keys."""
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "c1_l2",
+                          "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["higher_is_better"] is True and d["gpu_launches"] == 0
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "dtype", "data", "config",
+              "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "theano-variant" in d["config"]["workload"]
