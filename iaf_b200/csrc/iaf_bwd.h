@@ -1,0 +1,39 @@
+// Backward of the masked-AR stack / fused IAF step: internal interface used by iaf_capi.cu.
+#pragma once
+#include <algorithm>
+#include <cstring>
+#include <new>
+
+#include "iaf_common.h"
+
+struct IafBwdPlan;
+
+struct IafBwdArgs {
+  int mode;  // IAF_MODE_STEP | IAF_MODE_MULTICONV
+  int B;
+  const float* z;
+  const float* ctx;
+  // packed (masked, normalised) weights of the plan, one entry per stage (iaf_pack.cu layout)
+  const float* w_packed[IAF_MAX_STAGES];
+  const float* bias_packed[IAF_MAX_STAGES];
+  const float* padw_packed[IAF_MAX_STAGES];
+  // raw parameters, one entry per layer (hidden layers first, then heads), reference layouts
+  const float* const* w_raw;
+  const float* const* scale_raw;
+  // upstream gradients
+  const float* g_zout;   // step: [B,n_z,H,W]
+  const float* g_logsd;  // step: [B,n_z,H,W] or nullptr
+  const float* g_logdet; // step: [B] or nullptr
+  const float* g_heads[IAF_MAX_HEADS];  // multiconv: gradient of each head output
+  // results
+  float* g_z;
+  float* g_ctx;          // nullable
+  float* const* g_w;     // nullable (as arrays): raw-parameter gradients in the reference layouts
+  float* const* g_scale;
+  float* const* g_bias;
+};
+
+int iaf_bwd_plan_create(IafBwdPlan** out, const iaf_desc_t* d, const int* cin, const int* cout, const int* cout_pad,
+                        int head_pad);
+void iaf_bwd_plan_destroy(IafBwdPlan* p);
+int iaf_bwd_run(IafBwdPlan* p, const IafBwdArgs* a, cudaStream_t stream, int* n_launches);

@@ -8,6 +8,7 @@
 
 #include "iaf_common.h"
 #include "iaf_tc.h"
+#include "iaf_bwd.h"
 
 namespace {
 
@@ -77,6 +78,8 @@ struct iaf_plan {
   uint64_t submit_idx;
   // tensor-core path
   IafTcPlan* tc;
+  // backward (created on the first iaf_*_bwd call)
+  IafBwdPlan* bwd;
   uint64_t launches;
 };
 #define IAF_NSLOT 3
@@ -259,6 +262,7 @@ void iaf_plan_destroy(iaf_plan_t* pl) {
   if (pl->s_cmp) cudaStreamDestroy(pl->s_cmp);
   if (pl->s_d2h) cudaStreamDestroy(pl->s_d2h);
   if (pl->tc) iaf_tc_plan_destroy(pl->tc);
+  if (pl->bwd) iaf_bwd_plan_destroy(pl->bwd);
   delete pl;
 }
 
@@ -383,6 +387,63 @@ int iaf_layer_fwd(iaf_plan_t* pl, const float* eps, const float* post_mean, cons
   if (pl->d.n_heads != 2 || pl->d.head[0] != pl->d.n_z) return IAF_ERR_BAD_SHAPE;
   return run(pl, IAF_MODE_LAYER, eps, context, post_mean, post_logsd, prior_mean, prior_logsd, z_out, kl_out,
              nullptr, nullptr, kl_bc_out, kl_cost_out, B, (cudaStream_t)stream);
+}
+
+static int run_bwd(iaf_plan* pl, int mode, const float* z, const float* ctx, const float* const* w,
+                   const float* const* scale, const float* g_zout, const float* g_logsd, const float* g_logdet,
+                   const float* const* g_heads, float* g_z, float* g_ctx, float* const* g_w, float* const* g_scale,
+                   float* const* g_bias, int B, cudaStream_t stream) {
+  if (!pl->packed) return IAF_ERR_NOT_PACKED;
+  if (B <= 0) return IAF_ERR_BAD_ARG;
+  const iaf_desc_t& d = pl->d;
+  const int n_layers = d.n_hidden + d.n_heads;
+  const bool want_params = g_w || g_scale || g_bias;
+  if (want_params) {
+    if (!w || !scale) return IAF_ERR_BAD_ARG;
+    for (int i = 0; i < n_layers; ++i)
+      if (!w[i] || !scale[i]) return IAF_ERR_BAD_ARG;
+  }
+  if (!pl->bwd) {
+    int st = iaf_bwd_plan_create(&pl->bwd, &d, pl->cin, pl->cout, pl->cout_pad, pl->head_pad);
+    if (st != IAF_OK) return st == IAF_ERR_CUDA ? cuda_fail(cudaGetLastError(), "iaf_bwd_plan_create") : st;
+  }
+  IafBwdArgs a;
+  memset(&a, 0, sizeof(a));
+  a.mode = mode; a.B = B; a.z = z; a.ctx = ctx;
+  for (int j = 0; j < pl->n_stages; ++j) {
+    a.w_packed[j] = pl->w[j]; a.bias_packed[j] = pl->bias[j]; a.padw_packed[j] = pl->padw[j];
+  }
+  a.w_raw = w; a.scale_raw = scale;
+  a.g_zout = g_zout; a.g_logsd = g_logsd; a.g_logdet = g_logdet;
+  if (g_heads) { a.g_heads[0] = g_heads[0]; a.g_heads[1] = d.n_heads == 2 ? g_heads[1] : nullptr; }
+  a.g_z = g_z; a.g_ctx = d.n_hidden > 0 ? g_ctx : nullptr;
+  a.g_w = g_w; a.g_scale = g_scale; a.g_bias = g_bias;
+  int nl = 0;
+  int st = iaf_bwd_run(pl->bwd, &a, stream, &nl);
+  if (st == IAF_ERR_CUDA) return cuda_fail(cudaGetLastError(), "iaf_bwd_run");
+  pl->launches += nl;
+  return st;
+}
+
+int iaf_step_bwd(iaf_plan_t* pl, const float* z, const float* context, const float* const* w,
+                 const float* const* scale, const float* g_z_out, const float* g_logsd, const float* g_logdet,
+                 float* g_z, float* g_context, float* const* g_w, float* const* g_scale, float* const* g_bias, int B,
+                 void* stream) {
+  if (!pl || !z || !g_z_out || !g_z) return IAF_ERR_BAD_ARG;
+  if (pl->d.n_hidden > 0 && !context) return IAF_ERR_BAD_ARG;
+  if (pl->d.n_heads != 2 || pl->d.head[0] != pl->d.n_z) return IAF_ERR_BAD_SHAPE;
+  return run_bwd(pl, IAF_MODE_STEP, z, context, w, scale, g_z_out, g_logsd, g_logdet, nullptr, g_z, g_context, g_w,
+                 g_scale, g_bias, B, (cudaStream_t)stream);
+}
+
+int iaf_multiconv_bwd(iaf_plan_t* pl, const float* z, const float* context, const float* const* w,
+                      const float* const* scale, const float* const* g_outs, float* g_z, float* g_context,
+                      float* const* g_w, float* const* g_scale, float* const* g_bias, int B, void* stream) {
+  if (!pl || !z || !g_outs || !g_outs[0] || !g_z) return IAF_ERR_BAD_ARG;
+  if (pl->d.n_hidden > 0 && !context) return IAF_ERR_BAD_ARG;
+  if (pl->d.n_heads == 2 && !g_outs[1]) return IAF_ERR_BAD_ARG;
+  return run_bwd(pl, IAF_MODE_MULTICONV, z, context, w, scale, nullptr, nullptr, nullptr, g_outs, g_z, g_context, g_w,
+                 g_scale, g_bias, B, (cudaStream_t)stream);
 }
 
 int iaf_step_fwd_host(iaf_plan_t* pl, const float* z_host, const float* context_host, float* z_out_host,

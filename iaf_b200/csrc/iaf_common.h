@@ -1,6 +1,16 @@
 // Internal declarations shared by the CUDA translation units of libiaf_b200.so.
 #pragma once
+#ifdef IAF_EMU
+// Host emulation of the CUDA subset the SIMT kernels use (tests/emu/cuda_emu.h): TEST INFRASTRUCTURE ONLY, it lets the
+// CPU test-suite execute the kernels' index logic without a GPU.  Never compiled into libiaf_b200.so.
+#include "cuda_emu.h"
+#else
 #include <cuda_runtime.h>
+// kernel<<<grid, block, smem, stream>>>(args...) and the dynamic shared-memory window, spelled as macros so that the
+// same sources also compile under the host emulation above
+#define IAF_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define IAF_DYN_SMEM(type, name) extern __shared__ __align__(16) type name[]
+#endif
 #include <stdint.h>
 #include "../../include/iaf_b200.h"
 

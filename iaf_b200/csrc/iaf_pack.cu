@@ -79,6 +79,6 @@ __global__ void __launch_bounds__(128) iaf_pack_kernel(const __grid_constant__ I
 
 cudaError_t iaf_launch_pack(const IafPackParams& p, int max_cout, cudaStream_t stream) {
   dim3 grid(max_cout, p.n_layers);
-  iaf_pack_kernel<<<grid, 128, 0, stream>>>(p);
+  IAF_LAUNCH(iaf_pack_kernel, grid, 128, 0, stream, p);
   return cudaGetLastError();
 }

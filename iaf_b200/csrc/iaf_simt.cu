@@ -47,7 +47,7 @@ __device__ __forceinline__ float iaf_apply_nl(float v, int nl) {
   }
 
 __global__ void __launch_bounds__(IAF_SIMT_THREADS, 2) iaf_simt_kernel(const __grid_constant__ IafSimtParams p) {
-  extern __shared__ __align__(16) float smem[];
+  IAF_DYN_SMEM(float, smem);
   float* bufz = smem;
   float* bufa = bufz + p.bufz_elems;
   float* bufb = bufa + p.bufa_elems;
@@ -283,6 +283,6 @@ cudaError_t iaf_simt_set_smem(size_t smem_bytes) {
 }
 
 cudaError_t iaf_launch_simt(const IafSimtParams& p, size_t smem_bytes, cudaStream_t stream) {
-  iaf_simt_kernel<<<p.B * p.n_bands, IAF_SIMT_THREADS, smem_bytes, stream>>>(p);
+  IAF_LAUNCH(iaf_simt_kernel, p.B * p.n_bands, IAF_SIMT_THREADS, smem_bytes, stream, p);
   return cudaGetLastError();
 }

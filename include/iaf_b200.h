@@ -143,6 +143,32 @@ int iaf_layer_fwd(iaf_plan_t* plan, const float* eps, const float* post_mean, co
                   const float* prior_mean, const float* prior_logsd, const float* context,
                   float* z_out, float* kl_out, float* kl_bc_out, float* kl_cost_out, int B, void* stream);
 
+/*
+ * Backward of the fused step: what theano.grad / tf.gradients derive for
+ *   models.py:281-285 + ar.py:396-416   |   tf_train.py:69-72 + layers.py:158-166
+ * including the gradient through the in-graph weight normalisation and the mask, so masked
+ * taps receive exactly zero gradient (the contract postup() re-imposes, ar.py:369-373).
+ * Inputs: the forward's z and context (activations are recomputed, nothing is saved by
+ * iaf_step_fwd), the raw parameters w/scale as given to iaf_pack_weights (which must have
+ * been called with them), and the upstream gradients g_z_out [B,n_z,H,W], g_logsd
+ * [B,n_z,H,W] (may be NULL), g_logdet [B] (may be NULL).
+ * Outputs: g_z [B,n_z,H,W]; g_context [B,hidden[0],H,W] (may be NULL; untouched when
+ * n_hidden == 0); g_w/g_scale/g_bias: arrays of n_hidden + n_heads pointers in the
+ * reference layouts of the parameters (each array may be NULL: all three NULL skips the
+ * weight-gradient kernels).  Reductions are fixed-order: results are deterministic.
+ */
+int iaf_step_bwd(iaf_plan_t* plan, const float* z, const float* context, const float* const* w,
+                 const float* const* scale, const float* g_z_out, const float* g_logsd,
+                 const float* g_logdet, float* g_z, float* g_context, float* const* g_w,
+                 float* const* g_scale, float* const* g_bias, int B, void* stream);
+
+/* Backward of the un-fused operator iaf_multiconv_fwd: g_outs[k] [B,head[k],H,W] is the
+ * gradient at head k.  Same outputs as iaf_step_bwd. */
+int iaf_multiconv_bwd(iaf_plan_t* plan, const float* z, const float* context, const float* const* w,
+                      const float* const* scale, const float* const* g_outs, float* g_z,
+                      float* g_context, float* const* g_w, float* const* g_scale,
+                      float* const* g_bias, int B, void* stream);
+
 /* introspection */
 const char* iaf_strerror(int status);
 const char* iaf_last_cuda_error(void);          /* message of the last failing CUDA call (thread-local) */

@@ -1,0 +1,10 @@
+// Host-emulation build only (tests/emu): the tcgen05 path cannot be emulated, so the library reports it as unsupported
+// and every plan takes the SIMT path.  TEST INFRASTRUCTURE ONLY.
+#include "iaf_tc.h"
+
+bool iaf_tc_supported(const iaf_desc_t*) { return false; }
+int iaf_tc_plan_create(IafTcPlan**, const iaf_desc_t*) { return IAF_ERR_UNSUPPORTED; }
+void iaf_tc_plan_destroy(IafTcPlan*) {}
+int iaf_tc_pack(IafTcPlan*, const float* const*, const float* const*, const float* const*, cudaStream_t) { return IAF_ERR_UNSUPPORTED; }
+bool iaf_tc_mode_supported(const IafTcPlan*, int) { return false; }
+int iaf_tc_run(IafTcPlan*, const IafTcArgs*, cudaStream_t, int*) { return IAF_ERR_UNSUPPORTED; }

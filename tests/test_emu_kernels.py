@@ -1,0 +1,135 @@
+"""The SIMT kernels' logic under host emulation of CUDA (tests/emu/cuda_emu.h) against the oracle -- CPU only.
+
+The build container has no GPU; these tests compile iaf_capi.cu / iaf_pack.cu / iaf_simt.cu / iaf_bwd.cu with g++
+against an emulation of the CUDA subset they use and drive the SAME C ABI with numpy buffers, so the index arithmetic,
+shared-memory staging, barriers and fixed-order reductions of the forward SIMT kernel and of every backward kernel are
+executed and checked before GPU time is spent.  The `-m gpu` tests (tests/test_gpu_parity.py) repeat the same
+comparisons on the device through libiaf_b200.so; the emulated library is test infrastructure only and cannot be
+loaded by iaf_b200/.
+Reference for the gradients: torch autograd (fp64) through oracle/iaf_oracle_torch.py, i.e. what theano.grad /
+tf.gradients derive for models.py:281-285 + ar.py:396-416 | tf_train.py:69-72 + layers.py:158-166.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import iaf_oracle as O
+from oracle import iaf_oracle_torch as OT
+from tests.emu.harness import EmuOperator
+
+TOL = 2e-5  # fp32 kernels vs fp64 autograd, relative to the largest entry of each tensor
+
+
+def _keys(variant):
+    return ("V", "g", "b") if variant == "tf" else ("w", "s", "b")
+
+
+def _setup(variant, n_z, hidden, heads, H, W, B, nl):
+    hid, hd = O.make_params(variant, n_z, hidden, heads, seed=1)
+    z, ctx = O.make_inputs(B, n_z, hidden[0] if hidden else 1, H, W, seed=0)
+    layers = [tuple(l[k] for k in _keys(variant)) for l in hid + hd]
+    op = EmuOperator(variant, n_z, hidden, heads, H, W, nl=nl).set_weights(layers)
+    return op, hid, hd, z, (ctx if hidden else None)
+
+
+def _torch_params(hid, hd):
+    f64 = lambda ls: O.cast_params(ls, np.float64)
+    th, thh = OT.to_torch(f64(hid), torch.float64), OT.to_torch(f64(hd), torch.float64)
+    for l in th + thh:
+        for k in l:
+            l[k].requires_grad_(True)
+    return th, thh
+
+
+def _rel(a, b):
+    b = b.detach().numpy() if hasattr(b, "detach") else np.asarray(b)
+    assert np.isfinite(a).all()
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+STEP_CASES = [
+    # variant, n_z, hidden, H, W, B, nl
+    ("tf", 4, [8], 4, 4, 2, "elu"),
+    ("theano", 4, [8], 4, 4, 2, "elu"),
+    ("tf", 8, [16, 16], 5, 7, 2, "elu"),          # two hidden layers, non-square
+    ("theano", 8, [16, 16], 6, 9, 1, "softplus"),  # W > 8: two pixel segments; cvae1's default nl (models.py:384)
+    ("tf", 6, [12], 3, 5, 2, "tanh"),              # channel counts off the vector widths (padded head / hidden columns)
+    ("theano", 6, [12], 3, 5, 2, "relu"),
+    ("theano", 4, [], 4, 4, 2, "elu"),             # depth_ar = 0: no hidden layer, context unused
+    ("tf", 16, [80], 4, 4, 1, "elu"),              # > 64 channels: several ci / column blocks in the weight gradient
+    ("tf", 4, [8], 12, 24, 1, "leakyrelu"),        # several row bands in lconv and in the weight gradient
+    ("theano", 4, [4], 2, 2, 40, "elu"),           # more (sample, band) units than weight-gradient CTAs
+]
+
+
+@pytest.mark.parametrize("variant,n_z,hidden,H,W,B,nl", STEP_CASES)
+def test_emulated_step_forward_and_backward(variant, n_z, hidden, H, W, B, nl):
+    op, hid, hd, z, ctx = _setup(variant, n_z, hidden, [n_z, n_z], H, W, B, nl)
+    # forward (iaf_simt_kernel)
+    zo, ls, ld = op.step(z, ctx)
+    th, thh = _torch_params(hid, hd)
+    zt = torch.from_numpy(z).double().requires_grad_(True)
+    ct = torch.from_numpy(ctx).double().requires_grad_(True) if ctx is not None else None
+    zn, lsd, ldt = OT.iaf_step(variant, zt, ct, th, thh, nl=nl)
+    assert _rel(zo, zn) < 1e-5 and _rel(ls, lsd) < 1e-5 and _rel(ld, ldt) < 1e-5
+    # backward
+    rng = np.random.RandomState(5)
+    gzo, gls = rng.randn(*z.shape).astype(np.float32), rng.randn(*z.shape).astype(np.float32)
+    gld = rng.randn(B).astype(np.float32)
+    g_z, g_ctx, gw, gs, gb = op.step_bwd(z, ctx, gzo, gls, gld)
+    loss = (zn * torch.from_numpy(gzo)).sum() + (lsd * torch.from_numpy(gls)).sum() + (ldt * torch.from_numpy(gld)).sum()
+    loss.backward()
+    assert _rel(g_z, zt.grad) < TOL
+    if ctx is not None:
+        assert _rel(g_ctx, ct.grad) < TOL
+    for i, l in enumerate(th + thh):
+        for g, k in zip((gw[i], gs[i], gb[i]), _keys(variant)):
+            assert _rel(g, l[k].grad) < TOL, (i, k)
+    # masked taps get exactly zero (the postup contract, ar.py:369-373)
+    for i, l in enumerate(th + thh):
+        zd = i >= len(hidden)
+        if variant == "tf":
+            mask = O.get_conv_ar_mask(3, 3, gw[i].shape[2], gw[i].shape[3], zd)
+        else:
+            mask = O.theano_conv_ar_mask(gw[i].shape[1] - 1, gw[i].shape[0], (3, 3), zd)
+        assert (gw[i][mask == 0] == 0).all()
+
+
+def test_emulated_backward_optional_inputs_and_determinism():
+    op, hid, hd, z, ctx = _setup("tf", 4, [8], [4, 4], 4, 4, 3, "elu")
+    rng = np.random.RandomState(7)
+    gzo = rng.randn(*z.shape).astype(np.float32)
+    a = op.step_bwd(z, ctx, gzo, None, None)            # only z' has a gradient
+    b = op.step_bwd(z, ctx, gzo, None, None)
+    for x, y in zip([a[0], a[1]] + a[2] + a[3] + a[4], [b[0], b[1]] + b[2] + b[3] + b[4]):
+        assert np.array_equal(x, y)                        # fixed-order reductions
+    th, thh = _torch_params(hid, hd)
+    zt, ct = torch.from_numpy(z).double().requires_grad_(True), torch.from_numpy(ctx).double().requires_grad_(True)
+    zn, _, _ = OT.iaf_step("tf", zt, ct, th, thh)
+    (zn * torch.from_numpy(gzo)).sum().backward()
+    assert _rel(a[0], zt.grad) < TOL and _rel(a[1], ct.grad) < TOL
+    # input gradients only: the weight-gradient kernels are skipped, g_z / g_ctx unchanged
+    c = op.step_bwd(z, ctx, gzo, None, None, params=False)
+    assert np.array_equal(c[0], a[0]) and np.array_equal(c[1], a[1])
+
+
+@pytest.mark.parametrize("variant,heads", [("tf", [4, 4]), ("theano", [4, 4]), ("theano", [8]), ("theano", [6])])
+def test_emulated_multiconv_backward(variant, heads):
+    n_z, hidden, H, W, B = 4, [8], 4, 5, 2
+    if heads == [6]:
+        n_z, hidden = 6, [12]
+    op, hid, hd, z, ctx = _setup(variant, n_z, hidden, heads, H, W, B, "elu")
+    outs = op.multiconv(z, ctx)
+    th, thh = _torch_params(hid, hd)
+    zt, ct = torch.from_numpy(z).double().requires_grad_(True), torch.from_numpy(ctx).double().requires_grad_(True)
+    ref = OT.multiconv(variant, zt, ct, th, thh)
+    rng = np.random.RandomState(3)
+    g_outs = [rng.randn(*o.shape).astype(np.float32) for o in outs]
+    for o, r in zip(outs, ref):
+        assert _rel(o, r) < 1e-5
+    sum((r * torch.from_numpy(g)).sum() for r, g in zip(ref, g_outs)).backward()
+    g_z, g_ctx, gw, gs, gb = op.multiconv_bwd(z, ctx, g_outs)
+    assert _rel(g_z, zt.grad) < TOL and _rel(g_ctx, ct.grad) < TOL
+    for i, l in enumerate(th + thh):
+        for g, k in zip((gw[i], gs[i], gb[i]), _keys(variant)):
+            assert _rel(g, l[k].grad) < TOL, (i, k)
