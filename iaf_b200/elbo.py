@@ -174,6 +174,42 @@ class CudaIAF(object):
         return z, kl_bc, kl_cost
 
 
+class CudaIAFTrain(object):
+    """Differentiable iaf_layer for training: the posterior sample, logqs, prior logps and the KL sums are torch ops
+    (tf_train.py:56-85) around ``IAFOperator.step``, whose autograd node runs iaf_step_fwd / iaf_step_bwd
+    (SURVEY 8f-4).  ``obj.backward()`` on the result of forward() then yields the gradient of the training objective
+    with respect to every parameter, the masked-AR ones included (masked taps get exactly zero, ar.py:369-373)."""
+
+    def __init__(self, params, hps, path="auto"):
+        from .ops import IAFOperator
+        self.ops = {}
+        self.params, self.hps, self.path, self.IAFOperator = params, hps, path, IAFOperator
+
+    def __call__(self, scope, eps, post_mean, post_logsd, prior_mean, prior_logsd, context):
+        op = self.ops.get(scope)
+        zs, hs = self.hps["z_size"], self.hps["h_size"]
+        if op is None:
+            op = self.IAFOperator("tf", zs, [hs, hs], [zs, zs], nl="elu", path=self.path)
+            self.ops[scope] = op
+        pre = scope + "/ar_multiconv2d/"
+        op.set_weights([tuple(self.params[pre + n + "/" + k] for k in "Vgb")
+                        for n in ("layer_0", "layer_1", "layer_out_0", "layer_out_1")])
+        return stochastic_layer(lambda z, c: op.step(z, c, want_logdet=False)[:2], eps, post_mean, post_logsd, prior_mean,
+                                prior_logsd, context)
+
+
+def stochastic_layer(step, eps, post_mean, post_logsd, prior_mean, prior_logsd, context):
+    """tf_train.py:56-75 around a step callable (z, context) -> (z', arw_logsd): returns (z', kl_bc [B,C], kl_cost [B])."""
+    c = 0.5 * math.log(2.0 * math.pi)
+    z0 = post_mean + torch.exp(post_logsd) * eps                  # DiagonalGaussian.sample, distributions.py:20
+    logqs = -c - post_logsd - 0.5 * eps * eps                     # logps of the sample itself: (z0-mean)/sd == eps
+    z, arw_logsd = step(z0, context)
+    logqs = logqs + arw_logsd                                      # tf_train.py:72
+    logps = -c - prior_logsd - 0.5 * (z - prior_mean) ** 2 * torch.exp(-2.0 * prior_logsd)
+    kl = logqs - logps
+    return z, kl.sum(dim=(2, 3)), kl.sum(dim=(1, 2, 3))
+
+
 def sharded_bits_per_dim(params, x_uint8, noise, iaf_layer, hps, group=None):
     """Batch-sharded ELBO (BASELINE config C5; tf_train.py:126-142): every rank evaluates its contiguous slice of the
     global batch, and ONE sum all-reduce of the scalar loss gives the global bits/dim.  The free-bits batch mean stays

@@ -85,11 +85,18 @@ class IAFOperator(object):
         self._layers = out
         return self
 
-    def _weights_key(self):
-        return tuple((t.data_ptr(), t._version) for l in self._layers for t in l)
+    def _weights_key(self, layers=None):
+        return tuple((t.data_ptr(), t._version) for l in (self._layers if layers is None else layers) for t in l)
+
+    def _needs_grad(self, *tensors):
+        if not torch.is_grad_enabled():
+            return False
+        ts = [t for t in tensors if t is not None] + [t for l in (self._layers or []) for t in l]
+        return any(t.requires_grad for t in ts)
 
     # ---- plans ----------------------------------------------------------------------
-    def _plan(self, H, W, device):
+    def _plan(self, H, W, device, layers=None):
+        """Plan for (H, W, device) with the packed weights of ``layers`` (default: the current set_weights())."""
         key = (H, W, device.index)
         ent = self._plans.get(key)
         if ent is None:
@@ -110,12 +117,14 @@ class IAFOperator(object):
                 _lib.check(self._lib.iaf_plan_create(C.byref(handle), C.byref(d)))
             ent = [handle, None]
             self._plans[key] = ent
-        if self._layers is None:
+        if layers is None:
+            layers = self._layers
+        if layers is None:
             raise RuntimeError("IAFOperator.set_weights() has not been called")
-        wk = self._weights_key()
+        wk = self._weights_key(layers)
         if ent[1] != wk:
-            n = len(self._layers)
-            arr = lambda j: (C.c_void_p * n)(*[l[j].data_ptr() for l in self._layers])
+            n = len(layers)
+            arr = lambda j: (C.c_void_p * n)(*[l[j].data_ptr() for l in layers])
             with torch.cuda.device(device):
                 _lib.check(self._lib.iaf_pack_weights(ent[0], arr(0), arr(1), arr(2), _stream(device)))
             ent[1] = wk
@@ -156,7 +165,14 @@ class IAFOperator(object):
         return z, context, B, H, W
 
     def multiconv(self, z, context):
-        """The un-fused stack: list of head outputs (ar.py:396-416 / layers.py:158-166)."""
+        """The un-fused stack: list of head outputs (ar.py:396-416 / layers.py:158-166).  Differentiable: when an
+        input or a parameter requires grad the call is recorded for autograd (backward = iaf_multiconv_bwd)."""
+        if self._needs_grad(z, context):
+            flat = [t for l in self._layers for t in l]
+            return list(_MulticonvFn.apply(self, z, context if self.hidden else None, *flat))
+        return self._multiconv_raw(z, context)
+
+    def _multiconv_raw(self, z, context):
         z, context, B, H, W = self._shapes(z, context)
         plan = self._plan(H, W, z.device)
         outs = [torch.empty((B, h, H, W), device=z.device, dtype=torch.float32) for h in self.heads]
@@ -166,7 +182,15 @@ class IAFOperator(object):
         return outs
 
     def step(self, z, context, want_logsd=True, want_logdet=True):
-        """(z', arw_logsd [B,C,H,W], logdet [B]); logqs_new = logqs + arw_logsd."""
+        """(z', arw_logsd [B,C,H,W], logdet [B]); logqs_new = logqs + arw_logsd.  Differentiable: when an input or a
+        parameter requires grad the call is recorded for autograd (backward = iaf_step_bwd)."""
+        if self._needs_grad(z, context):
+            flat = [t for l in self._layers for t in l]
+            z_out, logsd, logdet = _StepFn.apply(self, z, context if self.hidden else None, *flat)
+            return z_out, (logsd if want_logsd else None), (logdet if want_logdet else None)
+        return self._step_raw(z, context, want_logsd, want_logdet)
+
+    def _step_raw(self, z, context, want_logsd=True, want_logdet=True):
         z, context, B, H, W = self._shapes(z, context)
         plan = self._plan(H, W, z.device)
         z_out = torch.empty_like(z)
@@ -222,6 +246,101 @@ class IAFOperator(object):
                                                _ptr(context), _ptr(z_out), _ptr(kl), _ptr(kl_bc), _ptr(kl_cost), B,
                                                _stream(eps.device)))
         return z_out, kl, kl_bc, kl_cost
+
+    # ---- backward -------------------------------------------------------
+    def _backward(self, kind, z, context, layers, grads_out, need_params):
+        """Shared driver of iaf_step_bwd / iaf_multiconv_bwd.  ``layers`` are the parameter tensors the forward
+        used; returns (g_z, g_context or None, [g_w], [g_scale], [g_bias]) (lists None when not needed)."""
+        z, context, B, H, W = self._shapes(z, context)
+        dev = z.device
+        plan = self._plan(H, W, dev, layers)
+        n = len(layers)
+        arr = lambda ts: (C.c_void_p * n)(*[t.data_ptr() for t in ts])
+        g_z = torch.empty_like(z)
+        g_ctx = torch.empty_like(context) if context is not None else None
+        gw = gs = gb = None
+        if need_params:
+            gw, gs, gb = ([torch.empty_like(l[j]) for l in layers] for j in range(3))
+        pa = lambda ts: arr(ts) if ts is not None else None
+        with torch.cuda.device(dev):
+            if kind == "step":
+                g_zout, g_logsd, g_logdet = grads_out
+                if g_zout is None:
+                    g_zout = torch.zeros_like(z)
+                g_zout, g_logsd, g_logdet = (None if t is None else _check_input(t, "grad") for t in (g_zout, g_logsd, g_logdet))
+                _lib.check(self._lib.iaf_step_bwd(plan, _ptr(z), _ptr(context), arr([l[0] for l in layers]),
+                                                  arr([l[1] for l in layers]), _ptr(g_zout), _ptr(g_logsd), _ptr(g_logdet),
+                                                  _ptr(g_z), _ptr(g_ctx), pa(gw), pa(gs), pa(gb), B, _stream(dev)))
+            else:
+                g_outs = [torch.zeros((B, h, H, W), device=dev) if g is None else _check_input(g, "grad")
+                          for g, h in zip(grads_out, self.heads)]
+                go = (C.c_void_p * len(g_outs))(*[g.data_ptr() for g in g_outs])
+                _lib.check(self._lib.iaf_multiconv_bwd(plan, _ptr(z), _ptr(context), arr([l[0] for l in layers]),
+                                                       arr([l[1] for l in layers]), go, _ptr(g_z), _ptr(g_ctx), pa(gw),
+                                                       pa(gs), pa(gb), B, _stream(dev)))
+        return g_z, g_ctx, gw, gs, gb
+
+    def step_backward(self, z, context, g_z_out, g_logsd=None, g_logdet=None, need_params=True):
+        """Explicit (non-autograd) entry to iaf_step_bwd with the current weights."""
+        return self._backward("step", z, context, self._layers, (g_z_out, g_logsd, g_logdet), need_params)
+
+
+def _regroup(flat):
+    return [tuple(flat[i:i + 3]) for i in range(0, len(flat), 3)]
+
+
+def _flat_param_grads(gw, gs, gb, n_layers):
+    if gw is None:
+        return [None] * (3 * n_layers)
+    return [t for i in range(n_layers) for t in (gw[i], gs[i], gb[i])]
+
+
+class _StepFn(torch.autograd.Function):
+    """autograd node of the fused step: forward = iaf_step_fwd, backward = iaf_step_bwd (activations recomputed)."""
+
+    @staticmethod
+    def forward(ctx, op, z, context, *flat):
+        with torch.no_grad():
+            out = op._step_raw(z, context, True, True)
+        ctx.op = op
+        ctx.has_ctx = context is not None
+        ctx.set_materialize_grads(False)  # unused outputs arrive as None, not as zero tensors
+        ctx.save_for_backward(z, *([context] if context is not None else []), *flat)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_zout, g_logsd, g_logdet):
+        saved = ctx.saved_tensors
+        z = saved[0]
+        context = saved[1] if ctx.has_ctx else None
+        flat = saved[2 if ctx.has_ctx else 1:]
+        need_params = any(ctx.needs_input_grad[3:])
+        g_z, g_ctx, gw, gs, gb = ctx.op._backward("step", z, context, _regroup(flat), (g_zout, g_logsd, g_logdet), need_params)
+        return (None, g_z, g_ctx) + tuple(_flat_param_grads(gw, gs, gb, len(flat) // 3))
+
+
+class _MulticonvFn(torch.autograd.Function):
+    """autograd node of the un-fused operator: forward = iaf_multiconv_fwd, backward = iaf_multiconv_bwd."""
+
+    @staticmethod
+    def forward(ctx, op, z, context, *flat):
+        with torch.no_grad():
+            outs = op._multiconv_raw(z, context)
+        ctx.op = op
+        ctx.has_ctx = context is not None
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(z, *([context] if context is not None else []), *flat)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *g_outs):
+        saved = ctx.saved_tensors
+        z = saved[0]
+        context = saved[1] if ctx.has_ctx else None
+        flat = saved[2 if ctx.has_ctx else 1:]
+        need_params = any(ctx.needs_input_grad[3:])
+        g_z, g_ctx, gw, gs, gb = ctx.op._backward("multiconv", z, context, _regroup(flat), g_outs, need_params)
+        return (None, g_z, g_ctx) + tuple(_flat_param_grads(gw, gs, gb, len(flat) // 3))
 
 
 # ------------------------------------------------------------------------------------

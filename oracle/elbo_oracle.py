@@ -23,6 +23,24 @@ class OracleIAF(object):
         return t(r["z"]), t(r["kl"].sum(axis=(2, 3))), t(r["kl_cost"])
 
 
+class TorchIAF(object):
+    """Differentiable oracle iaf_layer: the same block with oracle/iaf_oracle_torch.py ops on the parameters' own
+    dtype/device (float64 CPU in the tests), so torch autograd gives the reference gradient of the training objective
+    -- what tf.gradients derives in tf_train.py:222-232."""
+
+    def __init__(self, params, hps):
+        self.params, self.hps = params, hps
+
+    def __call__(self, scope, eps, post_mean, post_logsd, prior_mean, prior_logsd, context):
+        from . import iaf_oracle_torch as OT
+        from iaf_b200.elbo import stochastic_layer   # plain torch arithmetic shared with the product's training wrapper
+        pre = scope + "/ar_multiconv2d/"
+        layer = lambda n: {k: self.params[pre + n + "/" + k] for k in "Vgb"}
+        hidden, heads = [layer("layer_0"), layer("layer_1")], [layer("layer_out_0"), layer("layer_out_1")]
+        return stochastic_layer(lambda z, c: OT.iaf_step("tf", z, c, hidden, heads, "elu")[:2], eps, post_mean, post_logsd,
+                                prior_mean, prior_logsd, context)
+
+
 class OracleIAFTheano(object):
     """Theano front-end (models.py:273-298): parameters ``{name}_posterior_conv1_{k}_{w,s,b}`` / ``..._out_{k}_...``."""
 

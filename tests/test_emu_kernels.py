@@ -133,3 +133,70 @@ def test_emulated_multiconv_backward(variant, heads):
     for i, l in enumerate(th + thh):
         for g, k in zip((gw[i], gs[i], gb[i]), _keys(variant)):
             assert _rel(g, l[k].grad) < TOL, (i, k)
+
+
+def test_python_autograd_glue_over_the_emulated_abi(monkeypatch):
+    """iaf_b200.ops's autograd nodes (_StepFn / _MulticonvFn: argument order, saved tensors, None handling) exercised
+    on CPU tensors by pointing the ctypes binding at the emulated library.  Test-only monkeypatching: the product
+    refuses CPU tensors (see tests/test_host_cpu.py)."""
+    import contextlib
+    import ctypes as C
+    from iaf_b200 import _lib as L
+    from iaf_b200 import ops
+    from tests.emu.harness import emu
+
+    def check_input(t, name, shape=None):
+        assert isinstance(t, torch.Tensor) and t.dtype == torch.float32
+        if shape is not None:
+            assert tuple(t.shape) == tuple(shape)
+        return t.contiguous()
+
+    monkeypatch.setattr(L, "lib", emu)
+    monkeypatch.setattr(ops, "_check_input", check_input)
+    monkeypatch.setattr(ops, "_stream", lambda device: C.c_void_p(0))
+    monkeypatch.setattr(torch.cuda, "device", lambda d: contextlib.nullcontext())
+
+    variant, n_z, hidden, H, W, B = "tf", 4, [8], 4, 5, 2
+    hid, hd = O.make_params(variant, n_z, hidden, [n_z, n_z], seed=1)
+    z, ctx = O.make_inputs(B, n_z, hidden[0], H, W, seed=0)
+    dev = [tuple(torch.from_numpy(l[k].copy()).requires_grad_(True) for k in "Vgb") for l in hid + hd]
+    op = ops.IAFOperator(variant, n_z, hidden, [n_z, n_z], nl="elu", path="simt").set_weights(dev)
+    zg, cg = torch.from_numpy(z).requires_grad_(True), torch.from_numpy(ctx).requires_grad_(True)
+    th, thh = _torch_params(hid, hd)
+    zt, ct = torch.from_numpy(z).double().requires_grad_(True), torch.from_numpy(ctx).double().requires_grad_(True)
+
+    # step: only z' and logdet are used downstream (the logsd gradient arrives as None)
+    zo, ls, ld = op.step(zg, cg)
+    (zo.square().sum() + 3.0 * ld.sum()).backward()
+    zn, _, ldt = OT.iaf_step(variant, zt, ct, th, thh)
+    (zn.square().sum() + 3.0 * ldt.sum()).backward()
+    assert _rel(zg.grad.numpy(), zt.grad) < TOL and _rel(cg.grad.numpy(), ct.grad) < TOL
+    for i, l in enumerate(th + thh):
+        for t, k in zip(dev[i], "Vgb"):
+            assert _rel(t.grad.numpy(), l[k].grad) < TOL, (i, k)
+
+    # input gradients only (parameters frozen): the parameter-gradient outputs are skipped
+    frozen = [tuple(t.detach() for t in l) for l in dev]
+    op2 = ops.IAFOperator(variant, n_z, hidden, [n_z, n_z], nl="elu", path="simt").set_weights(frozen)
+    z2 = torch.from_numpy(z).requires_grad_(True)
+    op2.step(z2, torch.from_numpy(ctx))[0].square().sum().backward()
+    zt2 = torch.from_numpy(z).double().requires_grad_(True)
+    OT.iaf_step(variant, zt2, ct.detach(), [{k: v.detach() for k, v in l.items()} for l in th],
+                [{k: v.detach() for k, v in l.items()} for l in thh])[0].square().sum().backward()
+    assert _rel(z2.grad.numpy(), zt2.grad) < TOL
+
+    # un-fused operator, second head unused
+    for t in [zg, cg] + [t for l in dev for t in l]:
+        t.grad = None
+    m, s = op.multiconv(zg, cg)
+    m.sum().backward()
+    for t in [zt, ct] + [v for l in th + thh for v in l.values()]:
+        t.grad = None
+    OT.multiconv(variant, zt, ct, th, thh)[0].sum().backward()
+    assert _rel(zg.grad.numpy(), zt.grad) < TOL
+    assert _rel(dev[1][0].grad.numpy(), thh[0]["V"].grad) < TOL
+    assert float(dev[2][0].grad.abs().max()) == 0.0   # head 1 received no gradient
+
+    # no grad requested: plain call, nothing recorded
+    with torch.no_grad():
+        assert not op.step(zg, cg)[0].requires_grad
