@@ -106,6 +106,7 @@ struct IafTcParams {
   int flip, nl;
   float scale;
   int tmem_cols;
+  int prefetch;  // 0 off, 1: L2-prefetch this CTA's context range at kernel start, 2: context and z
   unsigned mg_sps, mg_wp, mg_win;  // magic multipliers for fast_div
 };
 
@@ -354,7 +355,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
       }
     }
   }
-  if (warp == TC_RED_WARP) asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (warp == TC_RED_WARP) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // Optional (IAF_TC_PREFETCH): pull this CTA's whole input range into L2 now, in tile order, so that the workers'
+    // per-phase global loads later hit L2 instead of paying an HBM round trip inside the L -> E0 -> E1 chain.  The
+    // samples a CTA touches are contiguous in NCHW, so the range is one block per tensor.
+    if (p.prefetch && nt > 0) {
+      const int n_first = fast_div(t0 * TC_TILE, p.SPS, p.mg_sps);
+      const int n_last = min(p.B - 1, fast_div(t1 * TC_TILE - 1, p.SPS, p.mg_sps));
+      const size_t c_bytes = (size_t)p.st[0].N * HW * 4, z_bytes = (size_t)p.C * HW * 4;
+      const int nsm = n_last - n_first + 1;
+      const uint32_t CH = 8192;
+      if (p.ctx && nst > 1) {
+        const uint8_t* base = reinterpret_cast<const uint8_t*>(p.ctx) + (size_t)n_first * c_bytes;
+        const size_t tot = (size_t)nsm * c_bytes;
+        for (size_t off = (size_t)lane * CH; off < tot; off += 32 * (size_t)CH) {
+          const uint32_t nb = (uint32_t)min((size_t)CH, tot - off);
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + off), "r"(nb) : "memory");
+        }
+      }
+      if (p.prefetch >= 2) {
+        const uint8_t* base = reinterpret_cast<const uint8_t*>(p.z) + (size_t)n_first * z_bytes;
+        const size_t tot = (size_t)nsm * z_bytes;
+        for (size_t off = (size_t)lane * CH; off < tot; off += 32 * (size_t)CH) {
+          const uint32_t nb = (uint32_t)min((size_t)CH, tot - off);
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + off), "r"(nb) : "memory");
+        }
+      }
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1234,6 +1263,7 @@ int iaf_tc_run(IafTcPlan* pl, const IafTcArgs* a, cudaStream_t stream, int* n_la
   p.flip = d.variant == IAF_VARIANT_THEANO ? 1 : 0;
   p.nl = d.nl; p.scale = 0.1f;
   p.tmem_cols = pl->tmem_cols;
+  { const char* pf = getenv("IAF_TC_PREFETCH"); p.prefetch = (pf && a->mode != IAF_MODE_LAYER) ? atoi(pf) : 0; }
   p.mg_sps = (unsigned)((1ULL << 32) / (unsigned)SPS) + 1u;
   p.mg_wp = (unsigned)((1ULL << 32) / (unsigned)p.Wp) + 1u;
   p.mg_win = (unsigned)((1ULL << 32) / (unsigned)p.WIN) + 1u;

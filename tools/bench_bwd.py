@@ -1,0 +1,52 @@
+"""Time the backward of the IAF step (iaf_step_bwd) on one GPU: CUDA events around K calls, inputs
+resident in HBM.  Prints one JSON line per workload.  Algorithmic flops of the backward = 3x the forward's live MACs
+(forward recompute + data gradient + weight gradient), fp32 FMA roofline (no tensor cores in this first version).
+usage: python tools/bench_bwd.py [c2a|c2b] [steps]"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from iaf_b200 import IAFOperator  # noqa: E402
+from oracle import iaf_oracle as O  # noqa: E402  (synthetic parameter / input generator only)
+
+WL = {"c2a": [64], "c2b": [160, 160]}
+
+
+def main():
+    wl = sys.argv[1] if len(sys.argv) > 1 else "c2a"
+    steps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+    hidden = WL[wl]
+    n_z, H, W, B = 32, 16, 16, 256
+    hid, hd = O.make_params("tf", n_z, hidden, [n_z, n_z], seed=1)
+    z, ctx = O.make_inputs(B, n_z, hidden[0], H, W, seed=0)
+    dev = [tuple(torch.from_numpy(np.ascontiguousarray(l[k])).cuda() for k in "Vgb") for l in hid + hd]
+    op = IAFOperator("tf", n_z, hidden, [n_z, n_z], nl="elu").set_weights(dev)
+    zg, cg = torch.from_numpy(z).cuda(), torch.from_numpy(ctx).cuda()
+    g1 = torch.randn_like(zg)
+    gl = torch.randn(B, device="cuda")
+    out = {}
+    for name, need in (("bwd_inputs_only", False), ("bwd_full", True)):
+        for _ in range(3):
+            op.step_backward(zg, cg, g1, g1, gl, need_params=need)
+        torch.cuda.synchronize()
+        l0 = op.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            op.step_backward(zg, cg, g1, g1, gl, need_params=need)
+        e1.record()
+        torch.cuda.synchronize()
+        out[name] = {"ms": e0.elapsed_time(e1) / steps, "launches_per_call": (op.launch_count() - l0) // steps}
+    fwd_flops = op.algorithmic_flops(B, H, W, "cuda:0")
+    full = out["bwd_full"]["ms"] * 1e-3
+    print(json.dumps({"workload": wl, "B": B, "steps": steps, **out,
+                      "algorithmic_flops_bwd": 3 * fwd_flops, "fp32_tflops": 3 * fwd_flops / full / 1e12,
+                      "latent_elems_per_s": B * n_z * H * W / full}))
+
+
+if __name__ == "__main__":
+    main()
