@@ -281,7 +281,7 @@ struct IafWgradParams {
   int B, H, W, cin, x_planes, ncol, g_planes;
   int flip, RB, n_bands, NG, n_cib, n_colb, PW;
 };
-__global__ void __launch_bounds__(BW_THREADS) iaf_bwd_wgrad_kernel(const __grid_constant__ IafWgradParams p) {
+__global__ void __launch_bounds__(BW_THREADS, 2) iaf_bwd_wgrad_kernel(const __grid_constant__ IafWgradParams p) {
   IAF_DYN_SMEM(float, sm);
   const int tid = threadIdx.x;
   const int H = p.H, W = p.W, HW = H * W, PW = p.PW;
@@ -536,7 +536,8 @@ struct IafBwdPlan {
   float* wT;                  // transposed weights of the current layer
   float* part;                // wgrad partials
   float* dwp[IAF_MAX_STAGES]; // reduced packed gradients per stage
-  int NG;
+  int NG[IAF_MAX_STAGES];      // weight-gradient CTAs per (ci block, column block) tile of each stage
+  int num_sms;
   size_t wg_smem; int wg_RB;
   size_t lc_smem_max;
 };
@@ -570,6 +571,12 @@ int iaf_bwd_plan_create(IafBwdPlan** out, const iaf_desc_t* d, const int* cin, c
     wt_max = std::max(wt_max, (size_t)IAF_NTAPS * cout_pad[j] * bw_round_up(cin[j], 8));
   }
   if (cudaMalloc(&pl->wT, sizeof(float) * wt_max) != cudaSuccess) { iaf_bwd_plan_destroy(pl); return IAF_ERR_CUDA; }
+  {
+    int dev = 0;
+    cudaDeviceProp prop;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { iaf_bwd_plan_destroy(pl); return IAF_ERR_CUDA; }
+    pl->num_sms = prop.multiProcessorCount;
+  }
   pl->nseg = (d->W + BW_PX - 1) / BW_PX;
   pl->P = BW_PX * pl->nseg + 2;
   if (pl->nseg > BW_THREADS) { iaf_bwd_plan_destroy(pl); return IAF_ERR_UNSUPPORTED; }
@@ -614,12 +621,16 @@ static int bw_ensure_scratch(IafBwdPlan* pl, int B) {
   if (cudaMalloc(&pl->hb, sizeof(float) * B * pl->ncol[last] * hw) != cudaSuccess) return IAF_ERR_CUDA;
   for (int a = 0; a < 2 && maxh; ++a)
     if (cudaMalloc(&pl->G[a], sizeof(float) * B * maxh * hw) != cudaSuccess) return IAF_ERR_CUDA;
+  // weight gradient: enough CTAs per tile to fill the machine twice over (the first version used a flat 32 and left
+  // C2a's 64x64 layers on 32 of 148 SMs: 1.76 ms; measured after: see DESIGN.md), never more than there are units
   const int n_bands = (pl->d.H + pl->wg_RB - 1) / pl->wg_RB;
-  pl->NG = std::max(1, std::min(B * n_bands, 32));
   size_t pmax = 0;
-  for (int j = 0; j < pl->n_stages; ++j)
-    pmax = std::max(pmax, (size_t)IAF_NTAPS * pl->cin[j] * pl->ncol[j] + 5 * (size_t)pl->ncol[j]);
-  if (cudaMalloc(&pl->part, sizeof(float) * pmax * pl->NG) != cudaSuccess) return IAF_ERR_CUDA;
+  for (int j = 0; j < pl->n_stages; ++j) {
+    const int tiles = ((pl->cin[j] + WG_T - 1) / WG_T) * ((pl->ncol[j] + WG_T - 1) / WG_T);
+    pl->NG[j] = std::max(1, std::min(std::min(B * n_bands, 512), (2 * pl->num_sms + tiles - 1) / tiles));
+    pmax = std::max(pmax, ((size_t)IAF_NTAPS * pl->cin[j] * pl->ncol[j] + 5 * (size_t)pl->ncol[j]) * pl->NG[j]);
+  }
+  if (cudaMalloc(&pl->part, sizeof(float) * pmax) != cudaSuccess) return IAF_ERR_CUDA;
   pl->scratch_B = B;
   return IAF_OK;
 }
@@ -711,13 +722,13 @@ int iaf_bwd_run(IafBwdPlan* pl, const IafBwdArgs* a, cudaStream_t stream, int* n
       memset(&q, 0, sizeof(q));
       q.x = xin; q.g = Gcur; q.part = pl->part;
       q.B = B; q.H = H; q.W = W; q.cin = pl->cin[j]; q.x_planes = pl->cin[j]; q.ncol = pl->ncol[j]; q.g_planes = g_planes;
-      q.flip = flip; q.RB = pl->wg_RB; q.n_bands = (H + pl->wg_RB - 1) / pl->wg_RB; q.NG = pl->NG;
+      q.flip = flip; q.RB = pl->wg_RB; q.n_bands = (H + pl->wg_RB - 1) / pl->wg_RB; q.NG = pl->NG[j];
       q.n_cib = (pl->cin[j] + WG_T - 1) / WG_T; q.n_colb = (pl->ncol[j] + WG_T - 1) / WG_T; q.PW = W + 2;
       IAF_LAUNCH(iaf_bwd_wgrad_kernel, q.n_cib * q.n_colb * q.NG, BW_THREADS, pl->wg_smem, stream, q);
       if (cudaGetLastError() != cudaSuccess) return IAF_ERR_CUDA;
       const int n = IAF_NTAPS * pl->cin[j] * pl->ncol[j] + 5 * pl->ncol[j];
       IAF_LAUNCH(iaf_bwd_reduce_kernel, ew_grid((size_t)n), BW_THREADS, 0, stream,
-                 (const float*)pl->part, pl->dwp[j], n, pl->NG);
+                 (const float*)pl->part, pl->dwp[j], n, pl->NG[j]);
       if (cudaGetLastError() != cudaSuccess) return IAF_ERR_CUDA;
       nl_ += 2;
     }

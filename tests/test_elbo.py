@@ -126,7 +126,10 @@ def test_training_objective_gradient_parity(hps, B):
     ref["obj"].backward()
     for k in pc:
         g, r = pg[k].grad, pc[k].grad
-        assert g is not None and r is not None, k
+        if r is None:   # e.g. the last up-layer's up_conv3: its output is discarded (tf_train.py:186-190)
+            assert g is None, k
+            continue
+        assert g is not None, k
         err = float((g.double().cpu() - r).abs().max()) / max(float(r.abs().max()), 1e-12)
         assert err < 2e-3, (k, err)   # fp32 plumbing (cuDNN convs) dominates; the operator's own gradients are
         #                               checked to 1e-4 in tests/test_gpu_parity.py
