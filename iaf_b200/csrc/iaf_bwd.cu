@@ -65,8 +65,8 @@ __device__ __forceinline__ float bw_nl_grad(float h, int nl) {
 
 #define BW_TAP(T, A, OFF)                                                                   \
   {                                                                                         \
-    const float4 wa = __ldg(reinterpret_cast<const float4*>(wrow + (size_t)(T) * tapstride));      \
-    const float4 wb = __ldg(reinterpret_cast<const float4*>(wrow + (size_t)(T) * tapstride) + 1);  \
+    const float4 wa = *reinterpret_cast<const float4*>(wrow + (T) * ncolb);                 \
+    const float4 wb = *reinterpret_cast<const float4*>(wrow + (T) * ncolb + 4);             \
     _Pragma("unroll") for (int j = 0; j < BW_PX; ++j) {                                     \
       const float a = A[j + (OFF)];                                                         \
       acc[j][0] = fmaf(a, wa.x, acc[j][0]); acc[j][1] = fmaf(a, wa.y, acc[j][1]);           \
@@ -78,7 +78,10 @@ __device__ __forceinline__ float bw_nl_grad(float h, int nl) {
 
 template <bool BWD>
 __global__ void __launch_bounds__(BW_THREADS) iaf_lconv_kernel(const __grid_constant__ IafLconvParams p) {
-  IAF_DYN_SMEM(float, sm);  // [CK][RB+1][P]
+  // [CK][RB+1][P] activations, then [CK][5][ncolb] weights of this CTA's column block.  (The first version read the
+  // weights with __ldg inside the channel loop: ncu showed the warps waiting on those loads, long-scoreboard stalls
+  // 3-5 per issued instruction and the FMA pipe 15-25 % busy; staged copies are read with broadcast LDS.128.)
+  IAF_DYN_SMEM(float, sm);
   const int tid = threadIdx.x;
   const int H = p.H, W = p.W, HW = H * W, P = p.P;
   int bid = blockIdx.x;
@@ -104,7 +107,8 @@ __global__ void __launch_bounds__(BW_THREADS) iaf_lconv_kernel(const __grid_cons
 #pragma unroll
     for (int c = 0; c < BW_CT; ++c) acc[j][c] = 0.f;
 
-  const size_t tapstride = (size_t)p.cin * p.ncol;
+  const int ncolb = p.nctb * BW_CT;
+  float* sw = sm + (size_t)p.CK * plane;
   // smem row slot l holds image row r0 + l (fwd: rows y, y+1) or r0 - 1 + l (bwd: rows y-1, y); column c holds x = c - 1
   const int row_base = BWD ? r0 - 1 : r0;
   const int slotA = BWD ? yl + 1 : yl;   // row y
@@ -113,23 +117,45 @@ __global__ void __launch_bounds__(BW_THREADS) iaf_lconv_kernel(const __grid_cons
   for (int c0 = 0; c0 < p.cin; c0 += p.CK) {
     const int ck = min(p.CK, p.cin - c0);
     __syncthreads();  // the previous chunk has been consumed
-    for (int i = tid; i < ck * plane; i += BW_THREADS) {
-      const int col = i % P;
-      const int l = (i / P) % rows;
-      const int c = i / plane;
-      const int y = row_base + l, x = col - 1;
-      float v = 0.f;
-      if (y >= 0 && y < H && x >= 0 && x < W) {
-        const int pix = y * W + x;
-        v = __ldg(p.in + ((size_t)n * p.in_planes + c0 + c) * HW + (p.flip ? HW - 1 - pix : pix));
+    // global loads are issued in batches of 8 before their shared-memory stores, so their latencies overlap
+    for (int i0 = tid; i0 < ck * plane; i0 += BW_THREADS * 8) {
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int i = i0 + k * BW_THREADS;
+        const int col = i % P;
+        const int l = (i / P) % rows;
+        const int c = i / plane;
+        const int y = row_base + l, x = col - 1;
+        v[k] = 0.f;
+        if (i < ck * plane && y >= 0 && y < H && x >= 0 && x < W) {
+          const int pix = y * W + x;
+          v[k] = __ldg(p.in + ((size_t)n * p.in_planes + c0 + c) * HW + (p.flip ? HW - 1 - pix : pix));
+        }
       }
-      sm[i] = v;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int i = i0 + k * BW_THREADS;
+        if (i < ck * plane) sm[i] = v[k];
+      }
+    }
+    {
+      const int nb4 = ncolb >> 2;  // float4 groups per (channel, tap) row; ncol and ncolb are multiples of 8
+      for (int i = tid; i < ck * IAF_NTAPS * nb4; i += BW_THREADS) {
+        const int c4 = i % nb4;
+        const int t = (i / nb4) % IAF_NTAPS;
+        const int c = i / (nb4 * IAF_NTAPS);
+        const int gcol = cblk * ncolb + c4 * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gcol < p.ncol) v = __ldg(reinterpret_cast<const float4*>(p.w + ((size_t)t * p.cin + c0 + c) * p.ncol + gcol));
+        *reinterpret_cast<float4*>(sw + ((size_t)c * IAF_NTAPS + t) * ncolb + c4 * 4) = v;
+      }
     }
     __syncthreads();
     if (active) {
       const float* aAp = sm + slotA * P + seg * BW_PX;  // cols x0-1 .. x0+8
       const float* aBp = sm + slotB * P + seg * BW_PX;
-      const float* wrow = p.w + (size_t)c0 * p.ncol + ct * BW_CT;
+      const float* wrow = sw + ctl * BW_CT;
       for (int c = 0; c < ck; ++c) {
         float a0[BW_PX + 2], a1[BW_PX + 2];
 #pragma unroll
@@ -149,7 +175,7 @@ __global__ void __launch_bounds__(BW_THREADS) iaf_lconv_kernel(const __grid_cons
         }
         aAp += plane;
         aBp += plane;
-        wrow += p.ncol;
+        wrow += IAF_NTAPS * ncolb;
       }
     }
   }
@@ -273,6 +299,7 @@ __global__ void __launch_bounds__(BW_THREADS) iaf_bwd_scatter_kernel(const __gri
 // plus the bias and pad-channel column sums.  CTA tile 64 ci x 64 col, thread tile 4 x 4 x 5 taps.
 // ------------------------------------------------------------------------------------------
 #define WG_T 64
+#define WG_LB 4  // staging loads in flight per thread (8 spills at the 128-register cap of two CTAs per SM)
 #define WG_S 68  // smem row stride (floats): 16-byte aligned float4 reads, 4-way conflicts only on the staging stores
 struct IafWgradParams {
   const float* x;   // [B][x_planes][HW]  layer input
@@ -314,30 +341,49 @@ __global__ void __launch_bounds__(BW_THREADS, 2) iaf_bwd_wgrad_kernel(const __gr
     const int r0 = band * p.RB;
     const int R = min(p.RB, H - r0);
     __syncthreads();
-    for (int i = tid; i < WG_T * xpos; i += BW_THREADS) {
-      const int pos = i % xpos, c = i / xpos;
-      const int l = pos / PW, col = pos % PW;
-      const int y = r0 + l, x = col - 1;
-      const int ci = cib * WG_T + c;
-      float v = 0.f;
-      if (ci < p.cin && l <= R && y < H && x >= 0 && x < W) {
-        const int pix = y * W + x;
-        v = __ldg(p.x + ((size_t)n * p.x_planes + ci) * HW + (p.flip ? HW - 1 - pix : pix));
+    // global loads are issued in batches of WG_LB before their shared-memory stores, so their latencies overlap (the
+    // first version's load -> store loop left the kernel waiting on one HBM round trip per element: ncu long-scoreboard)
+    for (int i0 = tid; i0 < WG_T * xpos; i0 += BW_THREADS * WG_LB) {
+      float v[WG_LB];
+#pragma unroll
+      for (int k = 0; k < WG_LB; ++k) {
+        const int i = i0 + k * BW_THREADS;
+        const int pos = i % xpos, c = i / xpos;
+        const int l = pos / PW, col = pos % PW;
+        const int y = r0 + l, x = col - 1;
+        const int ci = cib * WG_T + c;
+        v[k] = 0.f;
+        if (i < WG_T * xpos && ci < p.cin && l <= R && y < H && x >= 0 && x < W) {
+          const int pix = y * W + x;
+          v[k] = __ldg(p.x + ((size_t)n * p.x_planes + ci) * HW + (p.flip ? HW - 1 - pix : pix));
+        }
       }
-      Xs[pos * WG_S + c] = v;
+#pragma unroll
+      for (int k = 0; k < WG_LB; ++k) {
+        const int i = i0 + k * BW_THREADS;
+        if (i < WG_T * xpos) Xs[(i % xpos) * WG_S + i / xpos] = v[k];
+      }
     }
     const int gpos = p.RB * W;
-    for (int i = tid; i < WG_T * gpos; i += BW_THREADS) {
-      const int pos = i % gpos, c = i / gpos;
-      const int l = pos / W, x = pos % W;
-      const int y = r0 + l;
-      const int col = colb * WG_T + c;
-      float v = 0.f;
-      if (col < p.g_planes && l < R) {
-        const int pix = y * W + x;
-        v = __ldg(p.g + ((size_t)n * p.g_planes + col) * HW + (p.flip ? HW - 1 - pix : pix));
+    for (int i0 = tid; i0 < WG_T * gpos; i0 += BW_THREADS * WG_LB) {
+      float v[WG_LB];
+#pragma unroll
+      for (int k = 0; k < WG_LB; ++k) {
+        const int i = i0 + k * BW_THREADS;
+        const int pos = i % gpos, c = i / gpos;
+        const int l = pos / W, x = pos % W;
+        const int col = colb * WG_T + c;
+        v[k] = 0.f;
+        if (i < WG_T * gpos && col < p.g_planes && l < R) {
+          const int pix = (r0 + l) * W + x;
+          v[k] = __ldg(p.g + ((size_t)n * p.g_planes + col) * HW + (p.flip ? HW - 1 - pix : pix));
+        }
       }
-      Gs[pos * WG_S + c] = v;
+#pragma unroll
+      for (int k = 0; k < WG_LB; ++k) {
+        const int i = i0 + k * BW_THREADS;
+        if (i < WG_T * gpos) Gs[(i % gpos) * WG_S + i / gpos] = v[k];
+      }
     }
     __syncthreads();
     for (int l = 0; l < R; ++l) {
@@ -590,8 +636,8 @@ int iaf_bwd_plan_create(IafBwdPlan** out, const iaf_desc_t* d, const int* cin, c
   if (!rb) { iaf_bwd_plan_destroy(pl); return IAF_ERR_UNSUPPORTED; }
   pl->wg_RB = rb;
   if (cudaFuncSetAttribute(iaf_bwd_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->wg_smem) != cudaSuccess ||
-      cudaFuncSetAttribute(iaf_lconv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) != cudaSuccess ||
-      cudaFuncSetAttribute(iaf_lconv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) != cudaSuccess) {
+      cudaFuncSetAttribute(iaf_lconv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess ||
+      cudaFuncSetAttribute(iaf_lconv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess) {
     iaf_bwd_plan_destroy(pl);
     return IAF_ERR_CUDA;
   }
@@ -646,16 +692,19 @@ static void bw_lconv_geom(const IafBwdPlan* pl, IafLconvParams* q, size_t* smem)
   q->n_cblk = (nct + nctb - 1) / nctb;
   q->RB = std::max(1, std::min(H, BW_THREADS / (q->nseg * nctb)));
   q->n_bands = (H + q->RB - 1) / q->RB;
-  const size_t plane = sizeof(float) * (size_t)(q->RB + 1) * q->P;
-  int ck = (int)std::min<size_t>(32, (40 * 1024) / plane);
+  // per staged input channel: one activation plane and 5 x (column block) weights; up to ~80 KB so that two CTAs fit an SM
+  const size_t per_c = sizeof(float) * ((size_t)(q->RB + 1) * q->P + (size_t)IAF_NTAPS * nctb * BW_CT);
+  int ck = (int)std::min<size_t>(32, (80 * 1024) / per_c);
   q->CK = std::max(1, ck);
-  *smem = plane * q->CK;
+  // keep the weight region 16-byte aligned: CK * plane floats must be a multiple of 4
+  while (q->CK > 1 && ((size_t)q->CK * (q->RB + 1) * q->P) % 4 != 0) --q->CK;
+  *smem = per_c * q->CK;
 }
 
 static int bw_lconv(const IafBwdPlan* pl, IafLconvParams& q, cudaStream_t stream) {
   size_t smem = 0;
   bw_lconv_geom(pl, &q, &smem);
-  if (smem > 64 * 1024) return IAF_ERR_UNSUPPORTED;
+  if (smem > 100 * 1024 || ((size_t)q.CK * (q.RB + 1) * q.P) % 4 != 0) return IAF_ERR_UNSUPPORTED;
   const int grid = q.B * q.n_bands * q.n_cblk;
   if (q.bwd) IAF_LAUNCH(iaf_lconv_kernel<true>, grid, BW_THREADS, smem, stream, q);
   else IAF_LAUNCH(iaf_lconv_kernel<false>, grid, BW_THREADS, smem, stream, q);
