@@ -137,3 +137,49 @@ def test_training_objective_gradient_parity(hps, B):
             zd = "layer_out" in k
             mask = O.get_conv_ar_mask(3, 3, g.shape[2], g.shape[3], zd)
             assert bool((g.cpu().numpy()[mask == 0] == 0).all())   # the postup contract (ar.py:369-373)
+
+
+def _dp_grad_worker(rank, world, port, q):
+    import os
+    import torch.distributed as dist
+    from iaf_b200.parallel import allreduce_grads, shard_range
+    from oracle.elbo_oracle import TorchIAF
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    hps = dict(z_size=4, h_size=8, depth=1, num_blocks=2, kl_min=0.0, image_size=8)
+    params, x, noise = _setup(hps, 4, 11, torch.float64, "cpu")
+    for v in params.values():
+        v.requires_grad_(True)
+    lo, hi = shard_range(4, rank, world)
+    out = elbo.forward(params, x[lo:hi], {k: v[lo:hi] for k, v in noise.items()}, TorchIAF(params, hps), hps)
+    out["obj"].backward()
+    allreduce_grads(params, average=False)
+    q.put((rank, {k: v.grad.numpy().copy() for k, v in params.items() if v.grad is not None}))
+    dist.destroy_process_group()
+
+
+def test_sharded_gradients_allreduce_equals_single_process_gloo_world2():
+    """Data-parallel training step on CPU (tf_train.py:126-147, common.py:78-115): with kl_min = 0 the objective is a
+    sum over samples, so the summed gradients of two half-batch ranks equal the full-batch gradient."""
+    import os
+    import torch.multiprocessing as mp
+    from oracle.elbo_oracle import TorchIAF
+    hps = dict(z_size=4, h_size=8, depth=1, num_blocks=2, kl_min=0.0, image_size=8)
+    params, x, noise = _setup(hps, 4, 11, torch.float64, "cpu")
+    for v in params.values():
+        v.requires_grad_(True)
+    elbo.forward(params, x, noise, TorchIAF(params, hps), hps)["obj"].backward()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + os.getpid() % 2000
+    ps = [ctx.Process(target=_dp_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted((q.get(timeout=180) for _ in ps), key=lambda t: t[0])
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, grads in res:
+        for k, g in grads.items():
+            np.testing.assert_allclose(g, params[k].grad.numpy(), rtol=1e-9, atol=1e-12)
