@@ -240,6 +240,7 @@ __device__ __forceinline__ int bw_head_col(int n_heads, int k, int c) { return n
 // step: hb holds the raw heads (m, s) on entry and (g_m, g_s) on exit; g_z receives the direct term
 struct IafAffineBwdParams {
   const float* z; const float* g_zout; const float* g_logsd; const float* g_logdet;
+  const float* z_out; const float* logsd;  // kept by the training forward; when given, hb is write-only
   float* hb; float* g_z;
   int B, C, HW, cp, head_pad;
   float scale;
@@ -258,10 +259,16 @@ __global__ void __launch_bounds__(BW_THREADS) iaf_bwd_affine_kernel(const __grid
       continue;
     }
     const size_t e = ((size_t)n * p.C + c) * p.HW + gp;
-    const float m = p.hb[om], s = p.hb[os];
     // z' = (z - scale*m) * exp(-scale*s); arw_logsd = scale*s; logdet = -sum(arw_logsd)   (models.py:282-285)
-    const float ex = expf(-p.scale * s);
-    const float zn = (__ldg(p.z + e) - p.scale * m) * ex;
+    float ex, zn;
+    if (p.z_out) {
+      ex = expf(-__ldg(p.logsd + e));
+      zn = __ldg(p.z_out + e);
+    } else {
+      const float m = p.hb[om], s = p.hb[os];
+      ex = expf(-p.scale * s);
+      zn = (__ldg(p.z + e) - p.scale * m) * ex;
+    }
     const float gzo = __ldg(p.g_zout + e);
     float gs = -p.scale * zn * gzo;
     if (p.g_logsd) gs += p.scale * __ldg(p.g_logsd + e);
@@ -448,10 +455,19 @@ __global__ void __launch_bounds__(BW_THREADS, 2) iaf_bwd_wgrad_kernel(const __gr
 }
 
 __global__ void __launch_bounds__(BW_THREADS) iaf_bwd_reduce_kernel(const float* part, float* out, int n, int NG) {
+  // fixed summation order (8 interleaved partial sums, then a fixed tree): deterministic, and 8 loads in flight per
+  // thread instead of a chain of NG dependent ones
   for (int i = blockIdx.x * BW_THREADS + threadIdx.x; i < n; i += gridDim.x * BW_THREADS) {
-    float s = 0.f;
-    for (int g = 0; g < NG; ++g) s += part[(size_t)g * n + i];
-    out[i] = s;
+    float s[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s[k] = 0.f;
+    int g = 0;
+    for (; g + 8 <= NG; g += 8) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s[k] += part[(size_t)(g + k) * n + i];
+    }
+    for (int k = 0; g < NG; ++g, ++k) s[k] += part[(size_t)g * n + i];
+    out[i] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
   }
 }
 
@@ -722,8 +738,14 @@ int iaf_bwd_run(IafBwdPlan* pl, const IafBwdArgs* a, cudaStream_t stream, int* n
   // elementwise kernels: grid-stride, at most 4 CTAs per SM on 148 SMs
   auto ew_grid = [](size_t total) { return (int)std::min<size_t>(592, (total + BW_THREADS - 1) / BW_THREADS); };
 
+  // activations: recomputed below, or the ones the training forward kept
+  const bool saved = a->have_saved && a->mode == IAF_MODE_STEP;
+  const float* hcur[IAF_MAX_STAGES];
+  for (int j = 1; j < nst; ++j) hcur[j] = saved ? a->h_saved[j - 1] : pl->h[j];
+  hcur[0] = a->z;
+
   // ---- 1. forward recompute, layer at a time ----
-  for (int j = 0; j < nst; ++j) {
+  for (int j = 0; j < nst && !saved; ++j) {
     IafLconvParams q;
     memset(&q, 0, sizeof(q));
     q.in = j == 0 ? a->z : pl->h[j];
@@ -745,6 +767,7 @@ int iaf_bwd_run(IafBwdPlan* pl, const IafBwdArgs* a, cudaStream_t stream, int* n
     IafAffineBwdParams q;
     memset(&q, 0, sizeof(q));
     q.z = a->z; q.g_zout = a->g_zout; q.g_logsd = a->g_logsd; q.g_logdet = a->g_logdet;
+    q.z_out = saved ? a->z_out_saved : nullptr; q.logsd = saved ? a->logsd_saved : nullptr;
     q.hb = pl->hb; q.g_z = a->g_z;
     q.B = B; q.C = d.n_z; q.HW = HW; q.cp = pl->ncol[last]; q.head_pad = pl->head_pad; q.scale = 0.1f;
     IAF_LAUNCH(iaf_bwd_affine_kernel, ew_grid((size_t)B * pl->head_pad * HW), BW_THREADS, 0, stream, q);
@@ -765,7 +788,7 @@ int iaf_bwd_run(IafBwdPlan* pl, const IafBwdArgs* a, cudaStream_t stream, int* n
   const float* Gcur = pl->hb;
   int g_planes = pl->ncol[last];
   for (int j = last; j >= 0; --j) {
-    const float* xin = j == 0 ? a->z : pl->h[j];
+    const float* xin = hcur[j];
     if (want_params) {
       IafWgradParams q;
       memset(&q, 0, sizeof(q));
@@ -800,7 +823,7 @@ int iaf_bwd_run(IafBwdPlan* pl, const IafBwdArgs* a, cudaStream_t stream, int* n
     if (j == 0) {
       q.epi = EPI_BWD_Z; q.out = a->g_z;
     } else {
-      q.epi = EPI_BWD_HIDDEN; q.hprev = pl->h[j];
+      q.epi = EPI_BWD_HIDDEN; q.hprev = hcur[j];
       Gnext = (j == 1 && a->g_ctx) ? a->g_ctx : pl->G[j & 1];  // the gradient at a_0 IS the context gradient
       q.out = Gnext;
     }

@@ -25,6 +25,11 @@ struct IafBwdArgs {
   const float* g_logsd;  // step: [B,n_z,H,W] or nullptr
   const float* g_logdet; // step: [B] or nullptr
   const float* g_heads[IAF_MAX_HEADS];  // multiconv: gradient of each head output
+  // activations kept by the training forward (iaf_step_fwd_train): when have_saved the recompute is skipped
+  int have_saved;
+  const float* z_out_saved;              // z'
+  const float* logsd_saved;              // arw_logsd
+  const float* h_saved[IAF_MAX_HIDDEN];  // h_{j+1} = output of hidden layer j
   // results
   float* g_z;
   float* g_ctx;          // nullable

@@ -314,7 +314,7 @@ int iaf_pack_weights(iaf_plan_t* pl, const float* const* w, const float* const* 
 static int run(iaf_plan* pl, int mode, const float* z, const float* ctx, const float* post_mean,
                const float* post_logsd, const float* prior_mean, const float* prior_logsd, float* z_out,
                float* elem_out, float* m_out, float* s_out, float* bc_out, float* persample_out, int B,
-               cudaStream_t stream) {
+               cudaStream_t stream, float* const* hid_out = nullptr) {
   if (!pl->packed) return IAF_ERR_NOT_PACKED;
   if (B <= 0) return IAF_ERR_BAD_ARG;
   const iaf_desc_t& d = pl->d;
@@ -325,6 +325,7 @@ static int run(iaf_plan* pl, int mode, const float* z, const float* ctx, const f
     a.prior_mean = prior_mean; a.prior_logsd = prior_logsd; a.z_out = z_out; a.elem_out = elem_out;
     if (mode == IAF_MODE_MULTICONV) { a.z_out = m_out; a.elem_out = s_out; }  // raw heads travel in the same slots
     a.bc_out = bc_out; a.persample_out = persample_out; a.B = B;
+    for (int j = 0; j < d.n_hidden && hid_out; ++j) a.hid_out[j] = hid_out[j];
     int nl = 0;
     int st = iaf_tc_run(pl->tc, &a, stream, &nl);
     if (st == IAF_ERR_CUDA) return cuda_fail(cudaGetLastError(), "iaf_tc_run");
@@ -341,6 +342,7 @@ static int run(iaf_plan* pl, int mode, const float* z, const float* ctx, const f
   p.z_out = z_out; p.logsd_out = elem_out; p.m_out = m_out; p.s_out = s_out;
   p.bc_out = bc_out; p.persample_out = persample_out;
   p.partial = pl->partial; p.counter = pl->counter;
+  for (int j = 0; j < d.n_hidden && hid_out; ++j) p.hid_out[j] = hid_out[j];
   for (int j = 0; j < pl->n_stages; ++j) {
     p.stage[j].w = pl->w[j];
     p.stage[j].bias = pl->bias[j];
@@ -389,10 +391,22 @@ int iaf_layer_fwd(iaf_plan_t* pl, const float* eps, const float* post_mean, cons
              nullptr, nullptr, kl_bc_out, kl_cost_out, B, (cudaStream_t)stream);
 }
 
+int iaf_step_fwd_train(iaf_plan_t* pl, const float* z, const float* context, float* z_out, float* logsd_out,
+                       float* logdet_out, float* const* hidden_out, int B, void* stream) {
+  if (!pl || !z || !z_out || !logsd_out) return IAF_ERR_BAD_ARG;
+  if (pl->d.n_hidden > 0 && (!context || !hidden_out)) return IAF_ERR_BAD_ARG;
+  for (int j = 0; j < pl->d.n_hidden; ++j)
+    if (!hidden_out[j]) return IAF_ERR_BAD_ARG;
+  if (pl->d.n_heads != 2 || pl->d.head[0] != pl->d.n_z) return IAF_ERR_BAD_SHAPE;
+  return run(pl, IAF_MODE_STEP, z, context, nullptr, nullptr, nullptr, nullptr, z_out, logsd_out, nullptr, nullptr,
+             nullptr, logdet_out, B, (cudaStream_t)stream, hidden_out);
+}
+
 static int run_bwd(iaf_plan* pl, int mode, const float* z, const float* ctx, const float* const* w,
                    const float* const* scale, const float* g_zout, const float* g_logsd, const float* g_logdet,
                    const float* const* g_heads, float* g_z, float* g_ctx, float* const* g_w, float* const* g_scale,
-                   float* const* g_bias, int B, cudaStream_t stream) {
+                   float* const* g_bias, int B, cudaStream_t stream, const float* z_out_saved = nullptr,
+                   const float* logsd_saved = nullptr, const float* const* hidden_saved = nullptr) {
   if (!pl->packed) return IAF_ERR_NOT_PACKED;
   if (B <= 0) return IAF_ERR_BAD_ARG;
   const iaf_desc_t& d = pl->d;
@@ -418,6 +432,9 @@ static int run_bwd(iaf_plan* pl, int mode, const float* z, const float* ctx, con
   if (g_heads) { a.g_heads[0] = g_heads[0]; a.g_heads[1] = d.n_heads == 2 ? g_heads[1] : nullptr; }
   a.g_z = g_z; a.g_ctx = d.n_hidden > 0 ? g_ctx : nullptr;
   a.g_w = g_w; a.g_scale = g_scale; a.g_bias = g_bias;
+  a.z_out_saved = z_out_saved; a.logsd_saved = logsd_saved;
+  for (int j = 0; j < d.n_hidden && hidden_saved; ++j) a.h_saved[j] = hidden_saved[j];
+  a.have_saved = z_out_saved != nullptr;
   int nl = 0;
   int st = iaf_bwd_run(pl->bwd, &a, stream, &nl);
   if (st == IAF_ERR_CUDA) return cuda_fail(cudaGetLastError(), "iaf_bwd_run");
@@ -434,6 +451,19 @@ int iaf_step_bwd(iaf_plan_t* pl, const float* z, const float* context, const flo
   if (pl->d.n_heads != 2 || pl->d.head[0] != pl->d.n_z) return IAF_ERR_BAD_SHAPE;
   return run_bwd(pl, IAF_MODE_STEP, z, context, w, scale, g_z_out, g_logsd, g_logdet, nullptr, g_z, g_context, g_w,
                  g_scale, g_bias, B, (cudaStream_t)stream);
+}
+
+int iaf_step_bwd_saved(iaf_plan_t* pl, const float* z, const float* z_out, const float* logsd,
+                       const float* const* hidden, const float* const* w, const float* const* scale,
+                       const float* g_z_out, const float* g_logsd, const float* g_logdet, float* g_z, float* g_context,
+                       float* const* g_w, float* const* g_scale, float* const* g_bias, int B, void* stream) {
+  if (!pl || !z || !z_out || !logsd || !g_z_out || !g_z) return IAF_ERR_BAD_ARG;
+  if (pl->d.n_hidden > 0 && !hidden) return IAF_ERR_BAD_ARG;
+  for (int j = 0; j < pl->d.n_hidden; ++j)
+    if (!hidden[j]) return IAF_ERR_BAD_ARG;
+  if (pl->d.n_heads != 2 || pl->d.head[0] != pl->d.n_z) return IAF_ERR_BAD_SHAPE;
+  return run_bwd(pl, IAF_MODE_STEP, z, nullptr, w, scale, g_z_out, g_logsd, g_logdet, nullptr, g_z, g_context, g_w,
+                 g_scale, g_bias, B, (cudaStream_t)stream, z_out, logsd, hidden);
 }
 
 int iaf_multiconv_bwd(iaf_plan_t* pl, const float* z, const float* context, const float* const* w,

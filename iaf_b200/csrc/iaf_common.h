@@ -40,6 +40,7 @@ struct IafSimtParams {
   float* s_out;            // multiconv mode: head 1
   float* bc_out;           // layer mode: [B,C] sum over (h,w) of kl
   float* persample_out;    // step: logdet [B]; layer: kl_cost [B]
+  float* hid_out[IAF_MAX_HIDDEN];  // training forward: hidden activations [B][hidden[j]][HW], nullable
   float* partial;          // [B][n_bands][C] per-band per-channel partial sums
   unsigned* counter;       // [B] band arrival counters (self-resetting)
   IafStageDev stage[IAF_MAX_STAGES];

@@ -153,7 +153,10 @@ __global__ void __launch_bounds__(IAF_SIMT_THREADS, 2) iaf_simt_kernel(const __g
               if (byH || bxW) v += __ldg(S.padw + 3 * S.cout_pad + co);
             }
             if (js == 0) v += __ldg(p.ctx + ((size_t)n * S.cout + co) * HW + gp);  // ar.py:402 / layers.py:163
-            out[(co * rows_alloc + yl) * P + x + 1] = iaf_apply_nl(v, p.nl);
+            v = iaf_apply_nl(v, p.nl);
+            out[(co * rows_alloc + yl) * P + x + 1] = v;
+            // training forward: keep the activations (rows of this band only; halo rows belong to the next band)
+            if (p.hid_out[js] && yl < R) p.hid_out[js][((size_t)n * S.cout + co) * HW + gp] = v;
           }
         }
       } else {

@@ -75,6 +75,7 @@ struct IafTcStage {
   const __nv_bfloat16* wlo;
   const float* bias;         // [N] packed column order
   const float* padw;         // [4][N] or nullptr
+  float* hid_out;            // training forward: this (hidden) stage's activations, fp32 [B][N][HW]; nullptr = not kept
   int cin, N, K;
   int w_bytes;               // K*N*2
   int sm_whi, sm_wlo;        // smem byte offsets of the resident weight images
@@ -609,6 +610,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
                 }
                 v[e] = o * validf;
               }
+            }
+            if (St.hid_out && si.valid) {  // training forward: keep the activations for iaf_step_bwd_saved
+              float* hp = St.hid_out + ((size_t)si.n * St.N + c0) * HW + si.gp;
+#pragma unroll
+              for (int e = 0; e < 16; ++e) hp[(size_t)e * HW] = v[e];
             }
 #pragma unroll
             for (int hch = 0; hch < 2; ++hch) {
@@ -1251,6 +1257,7 @@ int iaf_tc_run(IafTcPlan* pl, const IafTcArgs* a, cudaStream_t stream, int* n_la
     IafTcStage& S_ = p.st[j];
     S_.whi = pl->whi[j]; S_.wlo = pl->wlo[j]; S_.bias = pl->bias[j];
     S_.padw = pl->padw[j];
+    S_.hid_out = (j < IAF_MAX_HIDDEN && j + 1 < pl->n_stages) ? a->hid_out[j] : nullptr;
     S_.cin = pl->cin[j]; S_.N = pl->N[j]; S_.K = pl->K[j];
     S_.w_bytes = pl->K[j] * pl->N[j] * 2;
     S_.sm_whi = pl->sm_whi[j]; S_.sm_wlo = pl->sm_wlo[j]; S_.sm_in = pl->sm_in[j];

@@ -16,6 +16,7 @@ struct IafTcArgs {
   float* elem_out;       // arw_logsd | kl, nullable
   float* bc_out;         // [B,C], nullable
   float* persample_out;  // [B], nullable
+  float* hid_out[IAF_MAX_HIDDEN];  // training forward: hidden activations [B][hidden[j]][HW], nullable
   int B;
 };
 

@@ -378,6 +378,11 @@ float v[16];
               v[e] = o * validf;
             }
           }
+          if (St.hid_out && si.valid && u < p.NT) {  // training forward: keep the activations for iaf_step_bwd_saved
+            float* hp = St.hid_out + ((size_t)si.n * St.N + c0) * HW + si.gp;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) hp[(size_t)e * HW] = v[e];
+          }
           if (u < p.NT) {
 #pragma unroll
             for (int hch = 0; hch < 2; ++hch) {

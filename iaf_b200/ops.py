@@ -201,6 +201,19 @@ class IAFOperator(object):
                                               B, _stream(z.device)))
         return z_out, logsd, logdet
 
+    def _step_train_raw(self, z, context):
+        """iaf_step_fwd_train: the step plus the hidden activations the backward needs (kept by the same kernels)."""
+        z, context, B, H, W = self._shapes(z, context)
+        plan = self._plan(H, W, z.device)
+        z_out, logsd = torch.empty_like(z), torch.empty_like(z)
+        logdet = torch.empty((B,), device=z.device, dtype=torch.float32)
+        hidden = [torch.empty((B, h, H, W), device=z.device, dtype=torch.float32) for h in self.hidden]
+        harr = (C.c_void_p * max(1, len(hidden)))(*[h.data_ptr() for h in hidden])
+        with torch.cuda.device(z.device):
+            _lib.check(self._lib.iaf_step_fwd_train(plan, _ptr(z), _ptr(context), _ptr(z_out), _ptr(logsd), _ptr(logdet),
+                                                    harr, B, _stream(z.device)))
+        return z_out, logsd, logdet, hidden
+
     def step_host(self, z, context, z_out, logsd_out, logdet_out):
         """End-to-end entry on HOST tensors (pinned or pageable): H2D, step, D2H, sync."""
         for t in (z, context, z_out, logsd_out, logdet_out):
@@ -248,9 +261,11 @@ class IAFOperator(object):
         return z_out, kl, kl_bc, kl_cost
 
     # ---- backward -------------------------------------------------------
-    def _backward(self, kind, z, context, layers, grads_out, need_params):
-        """Shared driver of iaf_step_bwd / iaf_multiconv_bwd.  ``layers`` are the parameter tensors the forward
-        used; returns (g_z, g_context or None, [g_w], [g_scale], [g_bias]) (lists None when not needed)."""
+    def _backward(self, kind, z, context, layers, grads_out, need_params, saved=None):
+        """Shared driver of iaf_step_bwd / iaf_step_bwd_saved / iaf_multiconv_bwd.  ``layers`` are the parameter
+        tensors the forward used; ``saved`` = (z_out, logsd, [hidden]) kept by iaf_step_fwd_train (then ``context``
+        is only a shape template for its gradient).  Returns (g_z, g_context or None, [g_w], [g_scale], [g_bias])
+        (lists None when not needed)."""
         z, context, B, H, W = self._shapes(z, context)
         dev = z.device
         plan = self._plan(H, W, dev, layers)
@@ -268,6 +283,14 @@ class IAFOperator(object):
                 if g_zout is None:
                     g_zout = torch.zeros_like(z)
                 g_zout, g_logsd, g_logdet = (None if t is None else _check_input(t, "grad") for t in (g_zout, g_logsd, g_logdet))
+                if saved is not None:
+                    z_out, logsd, hidden = saved
+                    harr = (C.c_void_p * max(1, len(hidden)))(*[h.data_ptr() for h in hidden])
+                    _lib.check(self._lib.iaf_step_bwd_saved(plan, _ptr(z), _ptr(z_out), _ptr(logsd), harr,
+                                                            arr([l[0] for l in layers]), arr([l[1] for l in layers]),
+                                                            _ptr(g_zout), _ptr(g_logsd), _ptr(g_logdet), _ptr(g_z),
+                                                            _ptr(g_ctx), pa(gw), pa(gs), pa(gb), B, _stream(dev)))
+                    return g_z, g_ctx, gw, gs, gb
                 _lib.check(self._lib.iaf_step_bwd(plan, _ptr(z), _ptr(context), arr([l[0] for l in layers]),
                                                   arr([l[1] for l in layers]), _ptr(g_zout), _ptr(g_logsd), _ptr(g_logdet),
                                                   _ptr(g_z), _ptr(g_ctx), pa(gw), pa(gs), pa(gb), B, _stream(dev)))
@@ -296,26 +319,33 @@ def _flat_param_grads(gw, gs, gb, n_layers):
 
 
 class _StepFn(torch.autograd.Function):
-    """autograd node of the fused step: forward = iaf_step_fwd, backward = iaf_step_bwd (activations recomputed)."""
+    """autograd node of the fused step: forward = iaf_step_fwd_train (the step's own kernels also keep the hidden
+    activations), backward = iaf_step_bwd_saved (no recompute)."""
 
     @staticmethod
     def forward(ctx, op, z, context, *flat):
         with torch.no_grad():
-            out = op._step_raw(z, context, True, True)
+            z_out, logsd, logdet, hidden = op._step_train_raw(z, context)
         ctx.op = op
         ctx.has_ctx = context is not None
+        ctx.n_hidden = len(hidden)
         ctx.set_materialize_grads(False)  # unused outputs arrive as None, not as zero tensors
-        ctx.save_for_backward(z, *([context] if context is not None else []), *flat)
-        return out
+        # the context itself is not needed by the backward (it only enters the forward); keep it as the shape template
+        ctx.save_for_backward(z, *([context] if context is not None else []), z_out, logsd, *hidden, *flat)
+        return z_out, logsd, logdet
 
     @staticmethod
     def backward(ctx, g_zout, g_logsd, g_logdet):
         saved = ctx.saved_tensors
         z = saved[0]
         context = saved[1] if ctx.has_ctx else None
-        flat = saved[2 if ctx.has_ctx else 1:]
+        i = 2 if ctx.has_ctx else 1
+        z_out, logsd = saved[i], saved[i + 1]
+        hidden = list(saved[i + 2:i + 2 + ctx.n_hidden])
+        flat = saved[i + 2 + ctx.n_hidden:]
         need_params = any(ctx.needs_input_grad[3:])
-        g_z, g_ctx, gw, gs, gb = ctx.op._backward("step", z, context, _regroup(flat), (g_zout, g_logsd, g_logdet), need_params)
+        g_z, g_ctx, gw, gs, gb = ctx.op._backward("step", z, context, _regroup(flat), (g_zout, g_logsd, g_logdet), need_params,
+                                                   saved=(z_out, logsd, hidden))
         return (None, g_z, g_ctx) + tuple(_flat_param_grads(gw, gs, gb, len(flat) // 3))
 
 

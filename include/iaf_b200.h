@@ -162,6 +162,23 @@ int iaf_step_bwd(iaf_plan_t* plan, const float* z, const float* context, const f
                  const float* g_logdet, float* g_z, float* g_context, float* const* g_w,
                  float* const* g_scale, float* const* g_bias, int B, void* stream);
 
+/*
+ * Training pair: iaf_step_fwd_train is iaf_step_fwd that ALSO writes the hidden activations
+ * (hidden_out[j] [B,hidden[j],H,W], j < n_hidden; the output of nl in ar.py:404 /
+ * layers.py:164) from inside the same kernels, and iaf_step_bwd_saved is iaf_step_bwd fed
+ * with them plus the forward's z_out / logsd_out instead of recomputing the stack (the
+ * context is not needed then: it only enters the forward).  This is what the python
+ * operator's autograd node uses.
+ */
+int iaf_step_fwd_train(iaf_plan_t* plan, const float* z, const float* context, float* z_out,
+                       float* logsd_out, float* logdet_out, float* const* hidden_out, int B,
+                       void* stream);
+int iaf_step_bwd_saved(iaf_plan_t* plan, const float* z, const float* z_out, const float* logsd,
+                       const float* const* hidden, const float* const* w,
+                       const float* const* scale, const float* g_z_out, const float* g_logsd,
+                       const float* g_logdet, float* g_z, float* g_context, float* const* g_w,
+                       float* const* g_scale, float* const* g_bias, int B, void* stream);
+
 /* Backward of the un-fused operator iaf_multiconv_fwd: g_outs[k] [B,head[k],H,W] is the
  * gradient at head k.  Same outputs as iaf_step_bwd. */
 int iaf_multiconv_bwd(iaf_plan_t* plan, const float* z, const float* context, const float* const* w,

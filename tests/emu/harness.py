@@ -98,6 +98,24 @@ class EmuOperator(object):
                                      _arr(gb) if params else None, B, None))
         return g_z, g_ctx, gw, gs, gb
 
+    def step_train(self, z, ctx):
+        B = z.shape[0]
+        zo, ls, ld = np.empty_like(z), np.empty_like(z), np.empty((B,), np.float32)
+        hidden = [np.full((B, h, self.H, self.W), np.nan, np.float32) for h in self.hidden]
+        harr = _arr(hidden) if hidden else None
+        _check(self.lib.iaf_step_fwd_train(self.plan, _p(z), _p(ctx), _p(zo), _p(ls), _p(ld), harr, B, None))
+        return zo, ls, ld, hidden
+
+    def step_bwd_saved(self, z, ctx_like, zo, ls, hidden, g_zout, g_logsd=None, g_logdet=None, params=True):
+        B = z.shape[0]
+        g_z, g_ctx, gw, gs, gb = self._grad_bufs(z, ctx_like, params)
+        harr = _arr(hidden) if hidden else None
+        _check(self.lib.iaf_step_bwd_saved(self.plan, _p(z), _p(zo), _p(ls), harr, _arr([l[0] for l in self.layers]),
+                                           _arr([l[1] for l in self.layers]), _p(g_zout), _p(g_logsd), _p(g_logdet),
+                                           _p(g_z), _p(g_ctx), _arr(gw) if params else None, _arr(gs) if params else None,
+                                           _arr(gb) if params else None, B, None))
+        return g_z, g_ctx, gw, gs, gb
+
     def multiconv_bwd(self, z, ctx, g_outs, params=True):
         B = z.shape[0]
         g_z, g_ctx, gw, gs, gb = self._grad_bufs(z, ctx, params)

@@ -85,6 +85,15 @@ def test_emulated_step_forward_and_backward(variant, n_z, hidden, H, W, B, nl):
     for i, l in enumerate(th + thh):
         for g, k in zip((gw[i], gs[i], gb[i]), _keys(variant)):
             assert _rel(g, l[k].grad) < TOL, (i, k)
+    # training pair: the forward kernel keeps the hidden activations, the backward uses them instead of recomputing
+    zo2, ls2, ld2, hs = op.step_train(z, ctx)
+    assert np.array_equal(zo2, zo) and np.array_equal(ls2, ls) and np.array_equal(ld2, ld)
+    assert all(np.isfinite(h).all() for h in hs)
+    s_z, s_ctx, sw, ss, sb = op.step_bwd_saved(z, ctx, zo2, ls2, hs, gzo, gls, gld)
+    assert _rel(s_z, zt.grad) < TOL and (ctx is None or _rel(s_ctx, ct.grad) < TOL)
+    for i, l in enumerate(th + thh):
+        for g, k in zip((sw[i], ss[i], sb[i]), _keys(variant)):
+            assert _rel(g, l[k].grad) < TOL, (i, k)
     # masked taps get exactly zero (the postup contract, ar.py:369-373)
     for i, l in enumerate(th + thh):
         zd = i >= len(hidden)

@@ -148,6 +148,16 @@ def test_backward_full_size_properties(hidden):
     for x, y, w_ in zip(flat(a), flat(c), flat(d)):
         ref = 2.0 * x.double() - 0.5 * y.double()
         assert float((w_.double() - ref).abs().max()) <= 1e-4 * max(float(ref.abs().max()), 1e-6)
+    # the autograd node (training forward on the tensor-core kernels keeps the activations, backward without recompute)
+    # agrees with the recompute path
+    zr, cr = zg.clone().requires_grad_(True), cg.clone().requires_grad_(True)
+    pr = [tuple(t.clone().requires_grad_(True) for t in l) for l in dev]
+    op2 = IAFOperator("tf", n_z, hidden, [n_z, n_z], nl="elu").set_weights(pr)
+    zo, ls, ld = op2.step(zr, cr)
+    ((zo * g1).sum() + (ld * l1).sum()).backward()
+    got = [zr.grad, cr.grad] + [l[0].grad for l in pr] + [l[1].grad for l in pr] + [l[2].grad for l in pr]
+    for x, y in zip(got, flat(a)):
+        assert float((x.double() - y.double()).abs().max()) <= 1e-4 * max(float(y.abs().max()), 1e-6)
     # sub-batches: input gradients bit-equal, parameter gradients add up
     h = B // 2
     lo = op.step_backward(zg[:h].contiguous(), cg[:h].contiguous(), g1[:h].contiguous(), None, l1[:h].contiguous())

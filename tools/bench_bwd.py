@@ -41,6 +41,29 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         out[name] = {"ms": e0.elapsed_time(e1) / steps, "launches_per_call": (op.launch_count() - l0) // steps}
+    # the training pair the autograd node uses: forward that keeps the activations + backward without recompute
+    for name, fn in (("fwd_plain", lambda: op._step_raw(zg, cg)), ("fwd_train", lambda: op._step_train_raw(zg, cg))):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        out[name] = {"ms": e0.elapsed_time(e1) / steps}
+    zo, ls, _, hs = op._step_train_raw(zg, cg)
+    for _ in range(3):
+        op._backward("step", zg, cg, op._layers, (g1, g1, gl), True, saved=(zo, ls, hs))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        op._backward("step", zg, cg, op._layers, (g1, g1, gl), True, saved=(zo, ls, hs))
+    e1.record()
+    torch.cuda.synchronize()
+    out["bwd_saved_full"] = {"ms": e0.elapsed_time(e1) / steps}
     fwd_flops = op.algorithmic_flops(B, H, W, "cuda:0")
     full = out["bwd_full"]["ms"] * 1e-3
     print(json.dumps({"workload": wl, "B": B, "steps": steps, **out,
