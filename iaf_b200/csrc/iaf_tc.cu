@@ -107,7 +107,8 @@ struct IafTcParams {
   int flip, nl;
   float scale;
   int tmem_cols;
-  int prefetch;  // 0 off, 1: L2-prefetch this CTA's context range at kernel start, 2: context and z
+  int prefetch;  // IAF_TC_PREFETCH: 1 bulk L2 prefetch of this CTA's context range at kernel start, 2: context and z,
+                 // 4: per-thread prefetch.global.L2 of the next tile's z window / context one period ahead
   unsigned mg_sps, mg_wp, mg_win;  // magic multipliers for fast_div
 };
 
@@ -199,6 +200,8 @@ __device__ __forceinline__ uint64_t mk_desc(uint32_t lo) { return ((uint64_t)UMM
 __device__ __forceinline__ uint32_t umma_idesc(int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_TILE >> 4) << 24);
 }
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // exp via ex2.approx.ftz (2 ulp): used where 1e-7-level error is far inside the 1e-4 parity budget
 __device__ __forceinline__ float fast_exp(float x) {
@@ -361,7 +364,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
     // Optional (IAF_TC_PREFETCH): pull this CTA's whole input range into L2 now, in tile order, so that the workers'
     // per-phase global loads later hit L2 instead of paying an HBM round trip inside the L -> E0 -> E1 chain.  The
     // samples a CTA touches are contiguous in NCHW, so the range is one block per tensor.
-    if (p.prefetch && nt > 0) {
+    if ((p.prefetch & 3) && nt > 0) {
       const int n_first = fast_div(t0 * TC_TILE, p.SPS, p.mg_sps);
       const int n_last = min(p.B - 1, fast_div(t1 * TC_TILE - 1, p.SPS, p.mg_sps));
       const size_t c_bytes = (size_t)p.st[0].N * HW * 4, z_bytes = (size_t)p.C * HW * 4;
@@ -375,7 +378,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
           asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + off), "r"(nb) : "memory");
         }
       }
-      if (p.prefetch >= 2) {
+      if ((p.prefetch & 3) >= 2) {
         const uint8_t* base = reinterpret_cast<const uint8_t*>(p.z) + (size_t)n_first * z_bytes;
         const size_t tot = (size_t)nsm * z_bytes;
         for (size_t off = (size_t)lane * CH; off < tot; off += 32 * (size_t)CH) {
@@ -507,6 +510,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
             }
           }
         }
+        if ((p.prefetch & 4) && kz + 1 < nt + nst - 1) {  // just-in-time L2 prefetch of the NEXT tile's z window
+#pragma unroll
+          for (int it = 0; it < TC_ZITEMS; ++it) {
+            const int idx = gtid + it * TC_GTHREADS;
+            if (idx < n_zitems) {
+              const int ch = fast_div(idx, p.WIN, p.mg_win);
+              const SlotInfo sn = decode_slot(p, (t0 + kz + 1) * TC_TILE + (idx - ch * p.WIN), HW);
+              if (sn.valid) {
+                const float* zp = p.z + ((size_t)sn.n * p.C + ch * 8) * HW + sn.gp;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) prefetch_l2(zp + (size_t)e * HW);
+              }
+            }
+          }
+        }
         if (gwarp == 0 && lane == 0) TL(1 + grp, 30, kz);
         if (kz >= 1) mbar_wait(&bars[BAR_ZEMPTY], (uint32_t)((kz - 1) & 1));  // M0(kz-1) has drained the window
         if (gwarp == 0 && lane == 0) TL(1 + grp, 31, kz);
@@ -547,6 +565,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
           uint8_t* obase = smem + Nx.sm_in + ((k & 1) * TC_TILE + sl) * 16;
           const bool mirror = ((k & 1) == 0) && (sl < p.MIR);
           bool waited = false;
+          if ((p.prefetch & 4) && j == 0 && k + 1 < nt + (nst - 1)) {  // just-in-time L2 prefetch of the NEXT tile's context
+            const SlotInfo sn = decode_slot(p, (u + 1) * TC_TILE + sl, HW);
+            if (sn.valid) {
+              for (int g = cg; g < ngroups; g += CGS) {
+                const float* cp = p.ctx + ((size_t)sn.n * St.N + g * 16) * HW + sn.gp;
+#pragma unroll
+                for (int e = 0; e < 16; ++e) prefetch_l2(cp + (size_t)e * HW);
+              }
+            }
+          }
           for (int g = cg; g < ngroups; g += CGS) {
             const int c0 = g * 16;
             float cx[16];
