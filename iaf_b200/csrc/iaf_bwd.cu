@@ -179,41 +179,51 @@ __global__ void __launch_bounds__(BW_THREADS) iaf_lconv_kernel(const __grid_cons
       }
     }
   }
-  if (!active) return;
-
-  const int y = r0 + yl;
-  const bool byH = (y == H - 1);
+  // ---- epilogue through shared memory: the register tile (8 px x 8 channels per thread) would store 4 bytes per lane
+  // 32 bytes apart; transposing it through smem lets consecutive lanes touch consecutive pixels of one channel, so the
+  // output stores and the context / activation loads of the epilogue are fully coalesced
+  const int NCS = ncolb + 4;  // tile row stride: [pixel][channel], 16-byte aligned rows
+  __syncthreads();            // every thread is done reading the staged chunk
+  if (active) {
 #pragma unroll
-  for (int j = 0; j < BW_PX; ++j) {
-    const int x = seg * BW_PX + j;
-    if (x >= W) continue;
-    const bool bx0 = (x == 0), bxW = (x == W - 1);
+    for (int j = 0; j < BW_PX; ++j) {
+      const int x = seg * BW_PX + j;
+      if (x >= W) continue;
+      float* tp = sm + (size_t)(yl * W + x) * NCS + ctl * BW_CT;
+      *reinterpret_cast<float4*>(tp) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+      *reinterpret_cast<float4*>(tp + 4) = make_float4(acc[j][4], acc[j][5], acc[j][6], acc[j][7]);
+    }
+  }
+  __syncthreads();
+  const int npix = R * W;
+  for (int i = tid; i < ncolb * npix; i += BW_THREADS) {
+    const int cl = i / npix, pos = i - cl * npix;
+    const int co = cblk * ncolb + cl;
+    if (co >= p.nout) continue;
+    const int ylp = pos / W, x = pos - ylp * W;
+    const int y = r0 + ylp;
+    const bool byH = (y == H - 1), bx0 = (x == 0), bxW = (x == W - 1);
     const int pix = y * W + x;
     const int gp = p.flip ? HW - 1 - pix : pix;
-#pragma unroll
-    for (int c = 0; c < BW_CT; ++c) {
-      const int co = ct * BW_CT + c;
-      if (co >= p.nout) continue;
-      float v = acc[j][c];
-      const size_t o = ((size_t)n * p.out_planes + co) * HW + gp;
-      if (p.epi == EPI_FWD_HIDDEN || p.epi == EPI_FWD_HEADS) {
-        v += __ldg(p.bias + co);
-        if (p.padw) {  // pad channel = 1 where the tap falls outside the image (conv.py:77-83)
-          if (bxW) v += __ldg(p.padw + co);
-          if (byH || bx0) v += __ldg(p.padw + p.ncol + co);
-          if (byH) v += __ldg(p.padw + 2 * p.ncol + co);
-          if (byH || bxW) v += __ldg(p.padw + 3 * p.ncol + co);
-        }
-        if (p.epi == EPI_FWD_HIDDEN) {
-          if (p.ctx) v += __ldg(p.ctx + o);  // out_planes == nout for hidden layers
-          v = bw_apply_nl(v, p.nl);
-        }
-        p.out[o] = v;
-      } else if (p.epi == EPI_BWD_HIDDEN) {
-        p.out[o] = v * bw_nl_grad(__ldg(p.hprev + o), p.nl);
-      } else {  // EPI_BWD_Z: the direct term exp(-arw_logsd) * g_z' is already there
-        p.out[o] = p.out[o] + v;
+    float v = sm[(size_t)pos * NCS + cl];
+    const size_t o = ((size_t)n * p.out_planes + co) * HW + gp;
+    if (p.epi == EPI_FWD_HIDDEN || p.epi == EPI_FWD_HEADS) {
+      v += __ldg(p.bias + co);
+      if (p.padw) {  // pad channel = 1 where the tap falls outside the image (conv.py:77-83)
+        if (bxW) v += __ldg(p.padw + co);
+        if (byH || bx0) v += __ldg(p.padw + p.ncol + co);
+        if (byH) v += __ldg(p.padw + 2 * p.ncol + co);
+        if (byH || bxW) v += __ldg(p.padw + 3 * p.ncol + co);
       }
+      if (p.epi == EPI_FWD_HIDDEN) {
+        if (p.ctx) v += __ldg(p.ctx + o);  // out_planes == nout for hidden layers
+        v = bw_apply_nl(v, p.nl);
+      }
+      p.out[o] = v;
+    } else if (p.epi == EPI_BWD_HIDDEN) {
+      p.out[o] = v * bw_nl_grad(__ldg(p.hprev + o), p.nl);
+    } else {  // EPI_BWD_Z: the direct term exp(-arw_logsd) * g_z' is already there
+      p.out[o] = p.out[o] + v;
     }
   }
 }
@@ -306,7 +316,6 @@ __global__ void __launch_bounds__(BW_THREADS) iaf_bwd_scatter_kernel(const __gri
 // plus the bias and pad-channel column sums.  CTA tile 64 ci x 64 col, thread tile 4 x 4 x 5 taps.
 // ------------------------------------------------------------------------------------------
 #define WG_T 64
-#define WG_LB 4  // staging loads in flight per thread (8 spills at the 128-register cap of two CTAs per SM)
 #define WG_S 68  // smem row stride (floats): 16-byte aligned float4 reads, 4-way conflicts only on the staging stores
 struct IafWgradParams {
   const float* x;   // [B][x_planes][HW]  layer input
@@ -320,8 +329,8 @@ __global__ void __launch_bounds__(BW_THREADS, 2) iaf_bwd_wgrad_kernel(const __gr
   const int tid = threadIdx.x;
   const int H = p.H, W = p.W, HW = H * W, PW = p.PW;
   const int xpos = (p.RB + 1) * PW;  // staged x positions: rows r0 .. r0+RB, cols -1 .. W
-  float* Xs = sm;                    // [xpos][WG_S]
-  float* Gs = sm + (size_t)xpos * WG_S;  // [RB*W][WG_S]
+  const int gpos = p.RB * W;
+  const size_t buf_floats = (size_t)(xpos + gpos) * WG_S;  // one stage: Xs [xpos][WG_S] then Gs [gpos][WG_S]
   int bid = blockIdx.x;
   const int colb = bid % p.n_colb; bid /= p.n_colb;
   const int cib = bid % p.n_cib;
@@ -342,57 +351,61 @@ __global__ void __launch_bounds__(BW_THREADS, 2) iaf_bwd_wgrad_kernel(const __gr
 #pragma unroll
     for (int b = 0; b < 4; ++b) sb[t][b] = 0.f;
 
-  const int units = p.B * p.n_bands;
-  for (int u = g; u < units; u += p.NG) {
+  // Asynchronous, double-buffered staging (cp.async, 4 bytes per element because the copy transposes [channel][pixel] ->
+  // [pixel][channel]): unit u+NG lands while unit u is being contracted.  Lane mapping inside a warp: 4 channels x 8
+  // consecutive pixels, i.e. four 32-byte global segments per warp-copy and 32 distinct shared-memory banks (row stride
+  // WG_S = 68 = 4 mod 32).  The first version staged with load -> store loops and spent about half its time waiting
+  // (ncu: FMA pipe 35-38 % busy, 1.1 M staging bank conflicts).
+  auto stage = [&](int u, float* buf) {
     const int n = u / p.n_bands, band = u % p.n_bands;
     const int r0 = band * p.RB;
     const int R = min(p.RB, H - r0);
-    __syncthreads();
-    // global loads are issued in batches of WG_LB before their shared-memory stores, so their latencies overlap (the
-    // first version's load -> store loop left the kernel waiting on one HBM round trip per element: ncu long-scoreboard)
-    for (int i0 = tid; i0 < WG_T * xpos; i0 += BW_THREADS * WG_LB) {
-      float v[WG_LB];
-#pragma unroll
-      for (int k = 0; k < WG_LB; ++k) {
-        const int i = i0 + k * BW_THREADS;
-        const int pos = i % xpos, c = i / xpos;
-        const int l = pos / PW, col = pos % PW;
-        const int y = r0 + l, x = col - 1;
-        const int ci = cib * WG_T + c;
-        v[k] = 0.f;
-        if (i < WG_T * xpos && ci < p.cin && l <= R && y < H && x >= 0 && x < W) {
-          const int pix = y * W + x;
-          v[k] = __ldg(p.x + ((size_t)n * p.x_planes + ci) * HW + (p.flip ? HW - 1 - pix : pix));
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < WG_LB; ++k) {
-        const int i = i0 + k * BW_THREADS;
-        if (i < WG_T * xpos) Xs[(i % xpos) * WG_S + i / xpos] = v[k];
-      }
+    float* Xs = buf;
+    float* Gs = buf + (size_t)xpos * WG_S;
+    const int nx = ((xpos + 7) >> 3) * (WG_T / 4) * 32;
+    for (int i = tid; i < nx; i += BW_THREADS) {
+      const int c_lo = i & 3, p_lo = (i >> 2) & 7, rest = i >> 5;
+      const int c = (rest % (WG_T / 4)) * 4 + c_lo, pos = (rest / (WG_T / 4)) * 8 + p_lo;
+      if (pos >= xpos) continue;
+      const int l = pos / PW, col = pos - l * PW;
+      const int y = r0 + l, x = col - 1;
+      const int ci = cib * WG_T + c;
+      const bool valid = ci < p.cin && l <= R && y < H && x >= 0 && x < W;
+      const int pix = valid ? y * W + x : 0;
+      const float* src = valid ? p.x + ((size_t)n * p.x_planes + ci) * HW + (p.flip ? HW - 1 - pix : pix) : p.x;
+      iaf_cp_async4(Xs + (size_t)pos * WG_S + c, src, valid);
     }
-    const int gpos = p.RB * W;
-    for (int i0 = tid; i0 < WG_T * gpos; i0 += BW_THREADS * WG_LB) {
-      float v[WG_LB];
-#pragma unroll
-      for (int k = 0; k < WG_LB; ++k) {
-        const int i = i0 + k * BW_THREADS;
-        const int pos = i % gpos, c = i / gpos;
-        const int l = pos / W, x = pos % W;
-        const int col = colb * WG_T + c;
-        v[k] = 0.f;
-        if (i < WG_T * gpos && col < p.g_planes && l < R) {
-          const int pix = (r0 + l) * W + x;
-          v[k] = __ldg(p.g + ((size_t)n * p.g_planes + col) * HW + (p.flip ? HW - 1 - pix : pix));
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < WG_LB; ++k) {
-        const int i = i0 + k * BW_THREADS;
-        if (i < WG_T * gpos) Gs[(i % gpos) * WG_S + i / gpos] = v[k];
-      }
+    const int ng = ((gpos + 7) >> 3) * (WG_T / 4) * 32;
+    for (int i = tid; i < ng; i += BW_THREADS) {
+      const int c_lo = i & 3, p_lo = (i >> 2) & 7, rest = i >> 5;
+      const int c = (rest % (WG_T / 4)) * 4 + c_lo, pos = (rest / (WG_T / 4)) * 8 + p_lo;
+      if (pos >= gpos) continue;
+      const int l = pos / W, x = pos - l * W;
+      const int col = colb * WG_T + c;
+      const bool valid = col < p.g_planes && l < R;
+      const int pix = valid ? (r0 + l) * W + x : 0;
+      const float* src = valid ? p.g + ((size_t)n * p.g_planes + col) * HW + (p.flip ? HW - 1 - pix : pix) : p.g;
+      iaf_cp_async4(Gs + (size_t)pos * WG_S + c, src, valid);
+    }
+    iaf_cp_async_commit();
+  };
+
+  const int units = p.B * p.n_bands;
+  if (g < units) stage(g, sm);
+  int it = 0;
+  for (int u = g; u < units; u += p.NG, ++it) {
+    const int un = u + p.NG;
+    if (un < units) {
+      stage(un, sm + (size_t)((it + 1) & 1) * buf_floats);
+      iaf_cp_async_wait<1>();  // everything but the newest group: unit u has landed
+    } else {
+      iaf_cp_async_wait<0>();
     }
     __syncthreads();
+    const float* Xs = sm + (size_t)(it & 1) * buf_floats;
+    const float* Gs = Xs + (size_t)xpos * WG_S;
+    const int r0 = (u % p.n_bands) * p.RB;
+    const int R = min(p.RB, H - r0);
     for (int l = 0; l < R; ++l) {
       const bool byH = (r0 + l == H - 1);
       for (int x = 0; x < W; ++x) {
@@ -427,6 +440,7 @@ __global__ void __launch_bounds__(BW_THREADS, 2) iaf_bwd_wgrad_kernel(const __gr
         }
       }
     }
+    __syncthreads();  // this buffer is refilled by the stage issued in the next iteration
   }
 
   const size_t nw = (size_t)IAF_NTAPS * p.cin * p.ncol;
@@ -642,14 +656,19 @@ int iaf_bwd_plan_create(IafBwdPlan** out, const iaf_desc_t* d, const int* cin, c
   pl->nseg = (d->W + BW_PX - 1) / BW_PX;
   pl->P = BW_PX * pl->nseg + 2;
   if (pl->nseg > BW_THREADS) { iaf_bwd_plan_destroy(pl); return IAF_ERR_UNSUPPORTED; }
-  // wgrad band: the largest band of rows whose staging fits 96 KB (two CTAs per SM), at least one row within 200 KB
+  // wgrad band: the largest band of rows whose TWO staging buffers fit 100 KB (two CTAs per SM), at least one row within 200 KB
   const int PW = d->W + 2;
   int rb = 0;
   for (int r = d->H; r >= 1; --r) {
-    const size_t s = sizeof(float) * WG_S * ((size_t)(r + 1) * PW + (size_t)r * d->W);
-    if (s <= 96 * 1024 || (r == 1 && s <= 200 * 1024)) { rb = r; pl->wg_smem = s; break; }
+    const size_t s = 2 * sizeof(float) * WG_S * ((size_t)(r + 1) * PW + (size_t)r * d->W);
+    if (s <= 100 * 1024 || (r == 1 && s <= 200 * 1024)) { rb = r; pl->wg_smem = s; break; }
   }
   if (!rb) { iaf_bwd_plan_destroy(pl); return IAF_ERR_UNSUPPORTED; }
+  {  // even bands: the same number of bands, all (but possibly the last) of equal height (16 rows: 4 x 4, not 5+5+5+1)
+    const int nb = (d->H + rb - 1) / rb;
+    rb = (d->H + nb - 1) / nb;
+    pl->wg_smem = 2 * sizeof(float) * WG_S * ((size_t)(rb + 1) * PW + (size_t)rb * d->W);
+  }
   pl->wg_RB = rb;
   if (cudaFuncSetAttribute(iaf_bwd_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->wg_smem) != cudaSuccess ||
       cudaFuncSetAttribute(iaf_lconv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess ||
@@ -714,7 +733,7 @@ static void bw_lconv_geom(const IafBwdPlan* pl, IafLconvParams* q, size_t* smem)
   q->CK = std::max(1, ck);
   // keep the weight region 16-byte aligned: CK * plane floats must be a multiple of 4
   while (q->CK > 1 && ((size_t)q->CK * (q->RB + 1) * q->P) % 4 != 0) --q->CK;
-  *smem = per_c * q->CK;
+  *smem = std::max(per_c * q->CK, sizeof(float) * (size_t)q->RB * pl->d.W * (nctb * BW_CT + 4));  // staging | output tile
 }
 
 static int bw_lconv(const IafBwdPlan* pl, IafLconvParams& q, cudaStream_t stream) {

@@ -10,6 +10,14 @@
 // same sources also compile under the host emulation above
 #define IAF_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define IAF_DYN_SMEM(type, name) extern __shared__ __align__(16) type name[]
+// 4-byte asynchronous global -> shared copy (LDGSTS), zero-filled when !valid; src must be a mapped address either way
+__device__ __forceinline__ void iaf_cp_async4(float* dst, const float* src, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  const int n = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void iaf_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void iaf_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 #endif
 #include <stdint.h>
 #include "../../include/iaf_b200.h"

@@ -54,6 +54,10 @@ inline std::barrier<>* g_bar = nullptr;
 #define gridDim (emu::g_gridDim)
 
 #define IAF_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emu::g_dyn_smem)
+// cp.async: the emulated copy completes at once (a superset of the device's ordering guarantees after wait + barrier)
+static inline void iaf_cp_async4(float* dst, const float* src, bool valid) { *dst = valid ? *src : 0.f; }
+static inline void iaf_cp_async_commit() {}
+template <int N> static inline void iaf_cp_async_wait() {}
 
 static inline void __syncthreads() { emu::g_bar->arrive_and_wait(); }
 static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
