@@ -79,6 +79,16 @@ class EmuOperator(object):
         _check(self.lib.iaf_multiconv_fwd(self.plan, _p(z), _p(ctx), _arr(outs), B, None))
         return outs
 
+    def layer(self, eps, post_mean, post_logsd, prior_mean, prior_logsd, ctx):
+        B = eps.shape[0]
+        f = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+        eps, post_mean, post_logsd, prior_mean, prior_logsd, ctx = map(f, (eps, post_mean, post_logsd, prior_mean, prior_logsd, ctx))
+        zo, kl = np.empty_like(eps), np.empty_like(eps)
+        kl_bc, kl_cost = np.empty((B, self.n_z), np.float32), np.empty((B,), np.float32)
+        _check(self.lib.iaf_layer_fwd(self.plan, _p(eps), _p(post_mean), _p(post_logsd), _p(prior_mean), _p(prior_logsd),
+                                      _p(ctx), _p(zo), _p(kl), _p(kl_bc), _p(kl_cost), B, None))
+        return zo, kl, kl_bc, kl_cost
+
     def _grad_bufs(self, z, ctx, params):
         g_z = np.full_like(z, np.nan)
         g_ctx = np.full_like(ctx, np.nan) if ctx is not None and self.hidden else None

@@ -209,3 +209,48 @@ def test_python_autograd_glue_over_the_emulated_abi(monkeypatch):
     # no grad requested: plain call, nothing recorded
     with torch.no_grad():
         assert not op.step(zg, cg)[0].requires_grad
+
+
+# ---------------------------------------------------------------------------------------
+# the forward SIMT kernel's source against the fixtures produced by executing the reference's own code
+# ---------------------------------------------------------------------------------------
+import os  # noqa: E402
+
+from tests.golden.cases import MULTICONV_CASES, case_inputs  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.mark.parametrize("ci", range(len(MULTICONV_CASES)), ids=[c[0] for c in MULTICONV_CASES])
+def test_emulated_multiconv_against_reference_fixtures(ci):
+    """iaf_multiconv_fwd (iaf_pack_kernel + iaf_simt_kernel under emulation) == what the reference's ar_multiconv2d /
+    multiconv2d source produced (tests/golden/make_golden.py); the GPU suite repeats this on the device."""
+    name, variant, B, n_z, hidden, H, W, nl = MULTICONV_CASES[ci]
+    g = np.load(os.path.join(GOLD, "multiconv.npz"))
+    hid, heads, z, ctx = case_inputs(variant, B, n_z, hidden, H, W, seed=ci)
+    layers = [tuple(l[k] for k in _keys(variant)) for l in hid + heads]
+    op = EmuOperator(variant, n_z, hidden, [n_z, n_z], H, W, nl=nl).set_weights(layers)
+    m, s = op.multiconv(z, ctx if hidden else None)
+    for got, ref in ((m, g[name + "_m"]), (s, g[name + "_s"])):
+        assert float(np.abs(got - ref).max() / max(np.abs(ref).max(), 1.0)) < 2e-5
+
+
+@pytest.mark.parametrize("name", ["kl0", "kl01", "kl5"])
+def test_emulated_fused_layer_against_iaflayer_down_fixture(name):
+    """iaf_layer_fwd (SIMT kernel, layer mode, under emulation) vs the tensors IAFLayer.down (tf_train.py:46-95, executed
+    from the reference source) produced: z', kl_cost and, through the rank-local free-bits rule, kl_obj."""
+    g = np.load(os.path.join(GOLD, "iaflayer_down.npz"))
+    v = lambda k: g[name + "_" + k]
+    hid, heads = O.make_params("tf", 4, [8, 8], [4, 4], seed=77)
+    layers = [tuple(l[k] for k in "Vgb") for l in hid + heads]
+    H, W = v("eps").shape[2:]
+    op = EmuOperator("tf", 4, [8, 8], [4, 4], H, W, nl="elu").set_weights(layers)
+    z1, kl, kl_bc, kl_cost = op.layer(v("eps"), v("rz_mean") + v("qz_mean"), v("rz_logsd") + v("qz_logsd"), v("pz_mean"),
+                                      v("pz_logsd"), v("up_context") + v("down_context"))
+    rel = lambda a, ref: float(np.abs(a - ref).max() / max(np.abs(ref).max(), 1.0))
+    assert rel(z1, (v("z0") - 0.1 * v("m")) / np.exp(0.1 * v("s"))) < 1e-5
+    assert rel(kl_cost, v("kl_cost")) < 1e-5
+    assert rel(kl.sum(axis=(2, 3)), kl_bc) < 1e-5
+    kl_min = float(v("kl_min"))
+    kl_obj = np.maximum(kl_bc.mean(axis=0, keepdims=True), kl_min).repeat(kl_bc.shape[0], 0).sum(axis=1) if kl_min > 0 else kl_cost
+    assert rel(kl_obj, v("kl_obj")) < 1e-5
