@@ -230,6 +230,27 @@ __device__ __forceinline__ float tc_apply_nl(float v, int nl) {
   }
 }
 
+// Packed fp32 pairs (sm_100: FADD2 / FMUL2 / FFMA2, one issue slot for two lanes' worth of work).  Only used by the
+// -DTC_FAST_EPI build of the epilogues (development variant for A/B: fewer worker instructions per tile; the default
+// build is the one every number in DESIGN.md was measured with).
+__device__ __forceinline__ void add2(float& a0, float& a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%0, %1};\n\tmov.b64 rb, {%2, %3};\n\tadd.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "+f"(a0), "+f"(a1) : "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void sub2(float& a0, float& a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%0, %1};\n\tmov.b64 rb, {%2, %3};\n\tsub.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "+f"(a0), "+f"(a1) : "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void mul2(float& a0, float& a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%0, %1};\n\tmov.b64 rb, {%2, %3};\n\tmul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "+f"(a0), "+f"(a1) : "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // split 8 floats into bf16 hi / lo and store both 16-byte vectors
 __device__ __forceinline__ void split_store8(const float* v, uint8_t* hi_ptr, uint8_t* lo_ptr) {
   uint32_t h[4], l[4];
@@ -237,7 +258,12 @@ __device__ __forceinline__ void split_store8(const float* v, uint8_t* hi_ptr, ui
   for (int i = 0; i < 4; ++i) {
     const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
     const uint32_t hb = *reinterpret_cast<const uint32_t*>(&hh);
+#ifdef TC_FAST_EPI
+    float r0 = v[2 * i], r1 = v[2 * i + 1];
+    sub2(r0, r1, __uint_as_float(hb << 16), __uint_as_float(hb & 0xFFFF0000u));
+#else
     const float r0 = v[2 * i] - __uint_as_float(hb << 16), r1 = v[2 * i + 1] - __uint_as_float(hb & 0xFFFF0000u);
+#endif
     const __nv_bfloat162 ll = __floats2bfloat162_rn(r0, r1);
     h[i] = hb;
     l[i] = *reinterpret_cast<const uint32_t*>(&ll);
@@ -598,6 +624,75 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
             uint32_t r[16];
             tmem_ld16(t_acc + (uint32_t)c0, r);
             tmem_ld_wait();
+#ifdef TC_FAST_EPI
+            float v[16];
+            if (NLT == IAF_NL_ELU && !PADW) {
+              // packed-pair arithmetic: accumulator halves, bias, context, elu(a) = max(a, exp(min(a,0)) - 1), validity
+              uint32_t r2[16];
+              if (St.merged) {
+                tmem_ld16(t_acc + (uint32_t)(St.N + c0), r2);
+                tmem_ld_wait();
+              }
+              const float4* tb4 = reinterpret_cast<const float4*>(tb + c0);
+              const float validf = si.valid ? 1.f : 0.f;
+#pragma unroll
+              for (int e4 = 0; e4 < 4; ++e4) {
+                const float4 t4 = tb4[e4];
+                const float bs[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {
+                  const int e = 4 * e4 + 2 * h2;
+                  float a0 = __uint_as_float(r[e]), a1 = __uint_as_float(r[e + 1]);
+                  if (St.merged) add2(a0, a1, __uint_as_float(r2[e]), __uint_as_float(r2[e + 1]));
+                  add2(a0, a1, bs[2 * h2], bs[2 * h2 + 1]);
+                  add2(a0, a1, cx[e], cx[e + 1]);
+                  float t0 = fminf(a0, 0.f), t1 = fminf(a1, 0.f);
+                  mul2(t0, t1, 1.4426950408889634f, 1.4426950408889634f);
+                  t0 = ex2_approx(t0); t1 = ex2_approx(t1);
+                  add2(t0, t1, -1.0f, -1.0f);
+                  float o0 = fmaxf(a0, t0), o1 = fmaxf(a1, t1);  // exp(a) - 1 >= a for a < 0, and = 0 <= a otherwise
+                  mul2(o0, o1, validf, validf);
+                  v[e] = o0; v[e + 1] = o1;
+                }
+              }
+            } else {
+              if (St.merged) {
+                uint32_t r2[16];
+                tmem_ld16(t_acc + (uint32_t)(St.N + c0), r2);
+                tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) + __uint_as_float(r2[e]));
+              }
+              const float4* tb4 = reinterpret_cast<const float4*>(tb + c0);
+              float bsv[16];
+#pragma unroll
+              for (int e4 = 0; e4 < 4; ++e4) {
+                const float4 t4 = tb4[e4];
+                bsv[4 * e4] = t4.x; bsv[4 * e4 + 1] = t4.y; bsv[4 * e4 + 2] = t4.z; bsv[4 * e4 + 3] = t4.w;
+              }
+              if (PADW) {
+                const float f1 = bxW ? 1.f : 0.f, f2 = (byH || bx0) ? 1.f : 0.f, f3 = byH ? 1.f : 0.f,
+                            f4 = (byH || bxW) ? 1.f : 0.f;
+#pragma unroll
+                for (int e = 0; e < 16; ++e)
+                  bsv[e] += f1 * tb[St.N + c0 + e] + f2 * tb[2 * St.N + c0 + e] + f3 * tb[3 * St.N + c0 + e] +
+                            f4 * tb[4 * St.N + c0 + e];
+              }
+              const float validf = si.valid ? 1.f : 0.f;
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                const float a = __uint_as_float(r[e]) + bsv[e] + cx[e];
+                float o;
+                if (NLT == IAF_NL_ELU) {
+                  const float ex = fast_exp(fminf(a, 0.f)) - 1.0f;
+                  o = a < 0.f ? ex : a;
+                } else {
+                  o = tc_apply_nl<NLT>(a, p.nl);
+                }
+                v[e] = o * validf;
+              }
+            }
+#else
             if (St.merged) {  // hi*lo partial products sit in columns [N, 2N)
               uint32_t r2[16];
               tmem_ld16(t_acc + (uint32_t)(St.N + c0), r2);
@@ -639,6 +734,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
                 v[e] = o * validf;
               }
             }
+#endif
             if (St.hid_out && si.valid) {  // training forward: keep the activations for iaf_step_bwd_saved
               float* hp = St.hid_out + ((size_t)si.n * St.N + c0) * HW + si.gp;
 #pragma unroll
@@ -699,13 +795,55 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
               uint32_t r2[16];
               tmem_ld16(t_acc + (uint32_t)(St.N + c0), r2);
               tmem_ld_wait();
+#ifdef TC_FAST_EPI
+#pragma unroll
+              for (int e = 0; e < 16; e += 2) {
+                float a0 = __uint_as_float(r[e]), a1 = __uint_as_float(r[e + 1]);
+                add2(a0, a1, __uint_as_float(r2[e]), __uint_as_float(r2[e + 1]));
+                r[e] = __float_as_uint(a0); r[e + 1] = __float_as_uint(a1);
+              }
+#else
 #pragma unroll
               for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) + __uint_as_float(r2[e]));
+#endif
             }
             if (MODE == IAF_MODE_LAYER) {
 #pragma unroll
               for (int i = 0; i < NRED; ++i) red[i] = 0.f;
             }
+#ifdef TC_FAST_EPI
+            if (MODE == IAF_MODE_STEP && !PADW) {
+              // packed-pair form of the step epilogue (same arithmetic; the per-thread sum is accumulated as two lanes)
+              if (si.valid) {
+                const float4* tb4 = reinterpret_cast<const float4*>(tb + c0);
+                const float4 bm0 = tb4[0], bm1 = tb4[1], bs0 = tb4[2], bs1 = tb4[3];
+                const float bm[8] = {bm0.x, bm0.y, bm0.z, bm0.w, bm1.x, bm1.y, bm1.z, bm1.w};
+                const float bs[8] = {bs0.x, bs0.y, bs0.z, bs0.w, bs1.x, bs1.y, bs1.z, bs1.w};
+                float rp0 = 0.f, rp1 = 0.f;
+#pragma unroll
+                for (int e = 0; e < 8; e += 2) {
+                  float m0 = __uint_as_float(r[e]), m1 = __uint_as_float(r[e + 1]);
+                  float s0 = __uint_as_float(r[8 + e]), s1 = __uint_as_float(r[9 + e]);
+                  add2(m0, m1, bm[e], bm[e + 1]);
+                  add2(s0, s1, bs[e], bs[e + 1]);
+                  mul2(m0, m1, p.scale, p.scale);   // arw_mean
+                  mul2(s0, s1, p.scale, p.scale);   // arw_logsd          (models.py:282-285)
+                  float d0 = zv[e], d1 = zv[e + 1];
+                  sub2(d0, d1, m0, m1);
+                  float t0 = s0, t1 = s1;
+                  mul2(t0, t1, -1.4426950408889634f, -1.4426950408889634f);
+                  t0 = ex2_approx(t0); t1 = ex2_approx(t1);
+                  mul2(d0, d1, t0, t1);             // z' = (z - arw_mean) * exp(-arw_logsd)
+                  const size_t ge = gi + (size_t)e * HW;
+                  p.z_out[ge] = d0;
+                  p.z_out[ge + HW] = d1;
+                  if (p.elem) { p.elem[ge] = s0; p.elem[ge + HW] = s1; }
+                  add2(rp0, rp1, s0, s1);
+                }
+                red[0] += rp0 + rp1;
+              }
+            } else
+#endif
             if (si.valid) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
