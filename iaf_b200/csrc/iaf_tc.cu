@@ -519,6 +519,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
             const int ch = fast_div(idx, p.WIN, p.mg_win);
             const int sl = idx - ch * p.WIN;
             dsto[it] = ch * plane + sl * 16;
+#ifdef TC_HALO_TRIM
+            // development variant: the extra (halo) tile of a two-stage stack only feeds the first MIR hidden slots of
+            // the next CTA's range, i.e. z slots [0, 2*MIR): the rest of its window is never consumed (rows of an MMA are
+            // independent), so it is neither loaded nor written
+            if (nst == 2 && kz == nt && sl >= 2 * p.MIR) { dsto[it] = -1; continue; }
+#endif
             const SlotInfo si = decode_slot(p, (t0 + kz) * TC_TILE + sl, HW);
             if (si.valid) {
               const size_t g = ((size_t)si.n * p.C + ch * 8) * HW + si.gp;
@@ -601,7 +607,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
               }
             }
           }
-          for (int g = cg; g < ngroups; g += CGS) {
+#ifdef TC_HALO_TRIM
+          // halo tile: only hidden slots [0, MIR) are consumed (by the heads of the last real tile); warps whose 32 slots
+          // lie beyond take part in the barrier protocol only
+          const bool trimw = (nst == 2 && k == nt && q * 32 >= p.MIR);
+#else
+          constexpr bool trimw = false;
+#endif
+          for (int g = trimw ? ngroups : cg; g < ngroups; g += CGS) {
             const int c0 = g * 16;
             float cx[16];
             if (j == 0 && si.valid) {  // += context   (ar.py:402 / layers.py:163)
