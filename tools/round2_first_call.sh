@@ -1,0 +1,25 @@
+#!/bin/bash
+# First GPU call of the next round (run under gpurun, ~4 min): confirms the tree, then A/Bs the two development variants
+# that were written after round 1's GPU budget ran out (tools/experiments/README.md) and takes a fresh capture of the
+# backward kernels.  Everything lands in gpurun_out/.
+set -u
+mkdir -p gpurun_out
+timeout 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 | tee gpurun_out/r2_gpu_tests.log
+build() {  # build <extra nvcc flags...>
+  (cd iaf_b200/csrc && nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 "$@" -shared -Xcompiler -fPIC \
+     -o ../lib/libiaf_b200.so iaf_capi.cu iaf_pack.cu iaf_simt.cu iaf_tc.cu iaf_bwd.cu 2>&1 | grep -E "error")
+}
+one() {  # one <label> <workload>
+  timeout 150 python bench.py --workload $2 --steps 300 --warmup 20 --no-cpu-baseline 2>&1 | tail -1 | \
+    python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$1', '$2', round(d['roofline']['kernel_us'],2))" | tee -a gpurun_out/r2_ab.log
+}
+for variant in "" "-DTC_FAST_EPI" "-DTC_HALO_TRIM" "-DTC_FAST_EPI -DTC_HALO_TRIM"; do
+  build $variant
+  one "[$variant]" c2a; one "[$variant]" c2a
+  if [ -n "$variant" ]; then
+    timeout 200 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -1 | sed "s/^/[$variant] parity: /" | tee -a gpurun_out/r2_ab.log
+  fi
+done
+build   # back to the default build
+timeout 200 ncu --set full --clock-control none --import-source on -k regex:'iaf_lconv|iaf_bwd_wgrad' -s 30 -c 5 -f \
+  -o gpurun_out/r2_bwd_c2a python tools/bench_bwd.py c2a 1 > gpurun_out/r2_ncu_bwd.log 2>&1
