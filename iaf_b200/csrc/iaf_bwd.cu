@@ -25,6 +25,34 @@
 
 enum { EPI_FWD_HIDDEN = 0, EPI_FWD_HEADS = 1, EPI_BWD_HIDDEN = 2, EPI_BWD_Z = 3 };
 
+// Division by a run-time constant in the staging / epilogue loops.  Default: the plain `/` (a ~25-instruction sequence
+// per quotient, two or three per staged element).  -DBW_FASTDIV (development variant, emulation-tested in
+// tests/test_emu_kernels.py, not yet timed on the GPU): multiply-high by a per-thread precomputed reciprocal.
+struct BwDiv {
+  int d;
+  unsigned m;
+};
+__device__ __forceinline__ BwDiv bw_mkdiv(int d) {
+  BwDiv f;
+  f.d = d;
+#ifdef BW_FASTDIV
+  f.m = d > 1 ? (unsigned)((1ull << 32) / (unsigned)d) + 1u : 0u;  // floor(2^32 / d) + 1: quotient at most one too large
+#else
+  f.m = 0u;
+#endif
+  return f;
+}
+__device__ __forceinline__ int bw_div(int s, const BwDiv& f) {  // 0 <= s < 2^31
+#ifdef BW_FASTDIV
+  if (f.d == 1) return s;
+  int q = (int)__umulhi((unsigned)s, f.m);
+  if (s - q * f.d < 0) --q;
+  return q;
+#else
+  return s / f.d;
+#endif
+}
+
 // ------------------------------------------------------------------------------------------
 // layer convolution, global -> global.  out[n, co, p] = epi( sum_t sum_ci in[n, ci, p +/- d_t] * w[t][ci][co] )
 // ------------------------------------------------------------------------------------------
@@ -109,6 +137,8 @@ __global__ void __launch_bounds__(BW_THREADS) iaf_lconv_kernel(const __grid_cons
 
   const int ncolb = p.nctb * BW_CT;
   float* sw = sm + (size_t)p.CK * plane;
+  const BwDiv dPlane = bw_mkdiv(plane), dP = bw_mkdiv(P), dW = bw_mkdiv(W), dNb4 = bw_mkdiv(ncolb >> 2),
+              dNb20 = bw_mkdiv((ncolb >> 2) * IAF_NTAPS);
   // smem row slot l holds image row r0 + l (fwd: rows y, y+1) or r0 - 1 + l (bwd: rows y-1, y); column c holds x = c - 1
   const int row_base = BWD ? r0 - 1 : r0;
   const int slotA = BWD ? yl + 1 : yl;   // row y
@@ -123,9 +153,10 @@ __global__ void __launch_bounds__(BW_THREADS) iaf_lconv_kernel(const __grid_cons
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const int i = i0 + k * BW_THREADS;
-        const int col = i % P;
-        const int l = (i / P) % rows;
-        const int c = i / plane;
+        const int c = bw_div(i, dPlane);
+        const int rem = i - c * plane;
+        const int l = bw_div(rem, dP);
+        const int col = rem - l * P;
         const int y = row_base + l, x = col - 1;
         v[k] = 0.f;
         if (i < ck * plane && y >= 0 && y < H && x >= 0 && x < W) {
@@ -142,9 +173,10 @@ __global__ void __launch_bounds__(BW_THREADS) iaf_lconv_kernel(const __grid_cons
     {
       const int nb4 = ncolb >> 2;  // float4 groups per (channel, tap) row; ncol and ncolb are multiples of 8
       for (int i = tid; i < ck * IAF_NTAPS * nb4; i += BW_THREADS) {
-        const int c4 = i % nb4;
-        const int t = (i / nb4) % IAF_NTAPS;
-        const int c = i / (nb4 * IAF_NTAPS);
+        const int c = bw_div(i, dNb20);
+        const int r2 = i - c * nb4 * IAF_NTAPS;
+        const int t = bw_div(r2, dNb4);
+        const int c4 = r2 - t * nb4;
         const int gcol = cblk * ncolb + c4 * 4;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (gcol < p.ncol) v = __ldg(reinterpret_cast<const float4*>(p.w + ((size_t)t * p.cin + c0 + c) * p.ncol + gcol));
@@ -196,11 +228,12 @@ __global__ void __launch_bounds__(BW_THREADS) iaf_lconv_kernel(const __grid_cons
   }
   __syncthreads();
   const int npix = R * W;
+  const BwDiv dNpix = bw_mkdiv(npix);
   for (int i = tid; i < ncolb * npix; i += BW_THREADS) {
-    const int cl = i / npix, pos = i - cl * npix;
+    const int cl = bw_div(i, dNpix), pos = i - cl * npix;
     const int co = cblk * ncolb + cl;
     if (co >= p.nout) continue;
-    const int ylp = pos / W, x = pos - ylp * W;
+    const int ylp = bw_div(pos, dW), x = pos - ylp * W;
     const int y = r0 + ylp;
     const bool byH = (y == H - 1), bx0 = (x == 0), bxW = (x == W - 1);
     const int pix = y * W + x;
@@ -331,6 +364,7 @@ __global__ void __launch_bounds__(BW_THREADS, 2) iaf_bwd_wgrad_kernel(const __gr
   const int xpos = (p.RB + 1) * PW;  // staged x positions: rows r0 .. r0+RB, cols -1 .. W
   const int gpos = p.RB * W;
   const size_t buf_floats = (size_t)(xpos + gpos) * WG_S;  // one stage: Xs [xpos][WG_S] then Gs [gpos][WG_S]
+  const BwDiv dPW = bw_mkdiv(PW), dWg = bw_mkdiv(W);
   int bid = blockIdx.x;
   const int colb = bid % p.n_colb; bid /= p.n_colb;
   const int cib = bid % p.n_cib;
@@ -367,7 +401,7 @@ __global__ void __launch_bounds__(BW_THREADS, 2) iaf_bwd_wgrad_kernel(const __gr
       const int c_lo = i & 3, p_lo = (i >> 2) & 7, rest = i >> 5;
       const int c = (rest % (WG_T / 4)) * 4 + c_lo, pos = (rest / (WG_T / 4)) * 8 + p_lo;
       if (pos >= xpos) continue;
-      const int l = pos / PW, col = pos - l * PW;
+      const int l = bw_div(pos, dPW), col = pos - l * PW;
       const int y = r0 + l, x = col - 1;
       const int ci = cib * WG_T + c;
       const bool valid = ci < p.cin && l <= R && y < H && x >= 0 && x < W;
@@ -380,7 +414,7 @@ __global__ void __launch_bounds__(BW_THREADS, 2) iaf_bwd_wgrad_kernel(const __gr
       const int c_lo = i & 3, p_lo = (i >> 2) & 7, rest = i >> 5;
       const int c = (rest % (WG_T / 4)) * 4 + c_lo, pos = (rest / (WG_T / 4)) * 8 + p_lo;
       if (pos >= gpos) continue;
-      const int l = pos / W, x = pos - l * W;
+      const int l = bw_div(pos, dWg), x = pos - l * W;
       const int col = colb * WG_T + c;
       const bool valid = col < p.g_planes && l < R;
       const int pix = valid ? (r0 + l) * W + x : 0;

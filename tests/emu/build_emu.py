@@ -7,7 +7,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "iaf_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
-LIB = os.path.join(OUT, "libiaf_emu.so")
+# IAF_EMU_FLAGS: extra -D switches, e.g. "-DBW_FASTDIV", to run the same tests on a development variant of the kernels
+EXTRA = os.environ.get("IAF_EMU_FLAGS", "").split()
+LIB = os.path.join(OUT, "libiaf_emu%s.so" % "".join(f.replace("-D", "_") for f in EXTRA))
 SOURCES = [os.path.join(CSRC, f) for f in ("iaf_capi.cu", "iaf_pack.cu", "iaf_simt.cu", "iaf_bwd.cu")] + \
           [os.path.join(HERE, "tc_stub.cc")]
 
@@ -27,7 +29,7 @@ def build(force=False):
         return LIB
     os.makedirs(OUT, exist_ok=True)
     cmd = ["g++", "-std=c++20", "-O2", "-g", "-fPIC", "-shared", "-pthread", "-DIAF_EMU", "-Wno-unknown-pragmas",
-           "-I", HERE, "-I", CSRC, "-o", LIB]
+           "-I", HERE, "-I", CSRC, "-o", LIB] + EXTRA
     for s in SOURCES:
         cmd += ["-x", "c++", s]
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -21,5 +21,10 @@ for variant in "" "-DTC_FAST_EPI" "-DTC_HALO_TRIM" "-DTC_FAST_EPI -DTC_HALO_TRIM
   fi
 done
 build   # back to the default build
+timeout 100 python tools/bench_bwd.py c2a 20 2>&1 | tail -1 | sed 's/^/[default] /' | tee -a gpurun_out/r2_ab.log
+build -DBW_FASTDIV
+timeout 100 python tools/bench_bwd.py c2a 20 2>&1 | tail -1 | sed 's/^/[-DBW_FASTDIV] /' | tee -a gpurun_out/r2_ab.log
+timeout 200 python -m pytest tests/test_gpu_backward.py -m gpu -x -q 2>&1 | tail -1 | sed 's/^/[-DBW_FASTDIV] backward parity: /' | tee -a gpurun_out/r2_ab.log
+build   # back to the default build
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:'iaf_lconv|iaf_bwd_wgrad' -s 30 -c 5 -f \
   -o gpurun_out/r2_bwd_c2a python tools/bench_bwd.py c2a 1 > gpurun_out/r2_ncu_bwd.log 2>&1
