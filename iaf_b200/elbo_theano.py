@@ -228,3 +228,29 @@ class CudaIAF(object):
         """up_iaf2_nl: the bare step (models.py:170-173) -> (z', arw_logsd)."""
         z_new, arw_logsd, _ = self._op(name, z.device).step(z, context)
         return z_new, arw_logsd
+
+
+class CudaIAFTrain(CudaIAF):
+    """Differentiable iaf_layer for training through the Theano front-end (what ``T.grad`` over cvae1's cost gives the
+    reference, graphy/misc/optim.py:99-123): the posterior sample, logqs, prior logps and the KL sums are torch ops
+    (models.py:273-298) around ``IAFOperator.step``, whose autograd node runs iaf_step_fwd_train / iaf_step_bwd_saved
+    (SURVEY 8f-4).  The parameter tensors are re-bound on every call so gradients flow to the entries of ``w``
+    (``{name}_posterior_conv1_{k}_w/_s/_b``), with masked taps at exactly zero (ar.py:369-373)."""
+
+    def _op(self, name, device):
+        op = self.ops.get(name)
+        nz, nh2, dar = self.hps["n_z"], self.hps["n_h2"], self.hps["depth_ar"]
+        if op is None:
+            op = self.IAFOperator("theano", nz, dar * [nh2], [nz, nz], nl=self.hps["nl"], path=self.path)   # models.py:92
+            self.ops[name] = op
+        pre = name + "_posterior_conv1"
+        names = ["%s_%d" % (pre, i) for i in range(dar)] + ["%s_out_%d" % (pre, k) for k in range(2)]
+        # the live tensors of w (float32, on the device): not detached, so their .grad is filled by backward()
+        op.set_weights([(self.w[n + "_w"], self.w[n + "_s"], self.w[n + "_b"]) for n in names])
+        return op
+
+    def __call__(self, name, eps, post_mean, post_logsd, prior_mean, prior_logsd, context):
+        from .elbo import stochastic_layer
+        op = self._op(name, eps.device)
+        return stochastic_layer(lambda z, c: op.step(z, c, want_logdet=False)[:2], eps, post_mean, post_logsd, prior_mean,
+                                prior_logsd, context)

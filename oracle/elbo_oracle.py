@@ -69,3 +69,27 @@ class OracleIAFTheano(object):
         z_new, arw_logsd, _ = O.iaf_step("theano", f(z), f(context), hidden, [layer("out_0"), layer("out_1")], self.hps["nl"])
         t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(z.dtype).to(z.device)
         return t(z_new), t(arw_logsd)
+
+
+class TorchIAFTheano(object):
+    """Differentiable oracle iaf_layer for the Theano front-end (models.py:273-298 / 169-178) with
+    oracle/iaf_oracle_torch.py ops on the parameters' own dtype (float64 CPU in the tests): torch autograd through it is
+    the reference for d(cost)/d(parameters), i.e. what ``T.grad`` derives in graphy/misc/optim.py:99-123."""
+
+    def __init__(self, w, hps):
+        self.w, self.hps = w, hps
+
+    def _layers(self, name):
+        pre = name + "_posterior_conv1_"
+        layer = lambda n: {k: self.w[pre + n + "_" + k] for k in "wsb"}
+        return [layer("%d" % k) for k in range(self.hps["depth_ar"])], [layer("out_0"), layer("out_1")]
+
+    def step(self, name, z, context):
+        from . import iaf_oracle_torch as OT
+        hidden, heads = self._layers(name)
+        return OT.iaf_step("theano", z, context, hidden, heads, self.hps["nl"])[:2]
+
+    def __call__(self, name, eps, post_mean, post_logsd, prior_mean, prior_logsd, context):
+        from iaf_b200.elbo import stochastic_layer   # plain torch arithmetic shared with the product's training wrapper
+        return stochastic_layer(lambda z, c: self.step(name, z, c), eps, post_mean, post_logsd, prior_mean, prior_logsd,
+                                context)

@@ -183,3 +183,48 @@ def test_sharded_gradients_allreduce_equals_single_process_gloo_world2():
     for _, grads in res:
         for k, g in grads.items():
             np.testing.assert_allclose(g, params[k].grad.numpy(), rtol=1e-9, atol=1e-12)
+
+
+def test_tf_training_gradients_over_the_emulated_abi(monkeypatch):
+    """CPU twin of test_training_objective_gradient_parity: elbo.CudaIAFTrain (autograd node -> iaf_step_fwd_train /
+    iaf_step_bwd_saved) with the ctypes binding pointed at the host-emulated library (tests/emu), against fp64 autograd
+    through the oracle block.  Test-only monkeypatching; the product refuses CPU tensors."""
+    import contextlib
+    import ctypes as C
+    from iaf_b200 import _lib as L
+    from iaf_b200 import ops
+    from oracle.elbo_oracle import TorchIAF
+    from tests.emu.harness import emu
+
+    def check_input(t, name, shape=None):
+        assert isinstance(t, torch.Tensor) and t.dtype == torch.float32
+        if shape is not None:
+            assert tuple(t.shape) == tuple(shape)
+        return t.contiguous()
+
+    monkeypatch.setattr(L, "lib", emu)
+    monkeypatch.setattr(ops, "_check_input", check_input)
+    monkeypatch.setattr(ops, "_stream", lambda device: C.c_void_p(0))
+    monkeypatch.setattr(torch.cuda, "device", lambda d: contextlib.nullcontext())
+
+    hps = dict(z_size=4, h_size=8, depth=1, num_blocks=2, kl_min=0.25, image_size=8)
+    p32, x, n32 = _setup(hps, 3, 9, torch.float32, "cpu")
+    p64, _, n64 = _setup(hps, 3, 9, torch.float64, "cpu")
+    for p in (p32, p64):
+        for v in p.values():
+            v.requires_grad_(True)
+    got = elbo.forward(p32, x, n32, elbo.CudaIAFTrain(p32, hps, path="simt"), hps)
+    ref = elbo.forward(p64, x, n64, TorchIAF(p64, hps), hps)
+    np.testing.assert_allclose(float(got["obj"].detach()), float(ref["obj"].detach()), rtol=2e-5)
+    got["obj"].backward()
+    ref["obj"].backward()
+    for k in p64:
+        g, r = p32[k].grad, p64[k].grad
+        if r is None:
+            assert g is None, k
+            continue
+        err = float((g.double() - r).abs().max()) / max(float(r.abs().max()), 1e-12)
+        assert err < 5e-4, (k, err)
+        if "ar_multiconv2d" in k and k.endswith("/V"):
+            mask = O.get_conv_ar_mask(3, 3, g.shape[2], g.shape[3], "layer_out" in k)
+            assert bool((g.numpy()[mask == 0] == 0).all()), k
