@@ -344,7 +344,34 @@ __global__ void __launch_bounds__(LY_THREADS, 1) iaf_ly_kernel(const __grid_cons
           uint32_t r[16];
           tmem_ld16(t_acc + (uint32_t)c0, r);
           tmem_ld_wait();
-float v[16];
+#ifdef TC_FAST_EPI
+          float v[16];
+          if (NLT == IAF_NL_ELU && !PADW) {  // packed-pair arithmetic, see iaf_tc_kernel
+            const float4* tb4 = reinterpret_cast<const float4*>(tb + c0);
+            const float validf = si.valid ? 1.f : 0.f;
+#pragma unroll
+            for (int e4 = 0; e4 < 4; ++e4) {
+              const float4 t4 = tb4[e4];
+              const float bs[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+              for (int h2 = 0; h2 < 2; ++h2) {
+                const int e = 4 * e4 + 2 * h2;
+                float a0 = __uint_as_float(r[e]), a1 = __uint_as_float(r[e + 1]);
+                add2(a0, a1, bs[2 * h2], bs[2 * h2 + 1]);
+                add2(a0, a1, cx[e], cx[e + 1]);
+                float t0 = fminf(a0, 0.f), t1 = fminf(a1, 0.f);
+                mul2(t0, t1, 1.4426950408889634f, 1.4426950408889634f);
+                t0 = ex2_approx(t0); t1 = ex2_approx(t1);
+                add2(t0, t1, -1.0f, -1.0f);
+                float o0 = fmaxf(a0, t0), o1 = fmaxf(a1, t1);
+                mul2(o0, o1, validf, validf);
+                v[e] = o0; v[e + 1] = o1;
+              }
+            }
+          } else
+#else
+          float v[16];
+#endif
           {
             // branch-free: bias rows come in as 16-byte vectors, the pad-channel terms (conv.py:77-83: the pad
             // channel is 1 where a tap falls outside the image) are 0/1-weighted FMAs, and an invalid slot
