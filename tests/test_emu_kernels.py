@@ -59,6 +59,8 @@ STEP_CASES = [
     ("tf", 16, [80], 4, 4, 1, "elu"),              # > 64 channels: several ci / column blocks in the weight gradient
     ("tf", 4, [8], 12, 24, 1, "leakyrelu"),        # several row bands in lconv and in the weight gradient
     ("theano", 4, [4], 2, 2, 40, "elu"),           # more (sample, band) units than weight-gradient CTAs
+    ("tf", 32, [64], 16, 16, 2, "elu"),            # C2a shape: the forward kernel splits the image into two row bands
+    #                                                (cross-band halo recompute, band partial sums, arrival counters)
 ]
 
 
