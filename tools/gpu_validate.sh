@@ -1,4 +1,6 @@
 #!/bin/bash
+# Full validation pass on the GPU box (run under gpurun): the whole -m gpu suite, the training-pair timings, both headline
+# bench lines, the launch list of the backward, and smoke().  Outputs land in gpurun_out/.
 mkdir -p gpurun_out
 ( time timeout 420 python -m pytest tests -m gpu -x -q ) 2>&1 | tail -12 | tee gpurun_out/gpu_tests_full.log
 timeout 100 python tools/bench_bwd.py c2a 20 2>&1 | tail -1 | tee gpurun_out/bench_bwd_c2a.json
