@@ -256,3 +256,44 @@ def test_emulated_fused_layer_against_iaflayer_down_fixture(name):
     kl_min = float(v("kl_min"))
     kl_obj = np.maximum(kl_bc.mean(axis=0, keepdims=True), kl_min).repeat(kl_bc.shape[0], 0).sum(axis=1) if kl_min > 0 else kl_cost
     assert rel(kl_obj, v("kl_obj")) < 1e-5
+
+
+def test_emulated_random_shapes_forward_and_both_backward_paths():
+    """Seeded random configurations (n_z down to 1, widening and narrowing hidden layers, 1 x N and N x 1 maps, every
+    nonlinearity, both variants): forward, backward with recompute and backward with kept activations, each against
+    fp64 autograd.  (tools-free twin of the ad-hoc stress runs of round 1: three seeds x 14 draws, worst error 1.5e-6.)"""
+    rng = np.random.RandomState(1)
+    done = 0
+    while done < 6:
+        variant = str(rng.choice(["tf", "theano"]))
+        n_z = int(rng.choice([1, 2, 3, 4, 6, 8]))
+        nh = int(rng.choice([0, 1, 2])) if variant == "theano" else int(rng.choice([1, 2]))
+        hidden, prev = [], n_z
+        for _ in range(nh):
+            prev = int(rng.choice([prev * k for k in (1, 2, 3)] + [prev // k for k in (2, 3) if prev % k == 0 and prev // k > 0]))
+            hidden.append(prev)
+        H, W = int(rng.choice([1, 2, 3, 5, 9, 17])), int(rng.choice([1, 2, 3, 7, 8, 9, 16, 17, 25]))
+        B, nl = int(rng.choice([1, 2, 3])), str(rng.choice(["elu", "softplus", "relu", "tanh", "leakyrelu"]))
+        if not (prev % n_z == 0 or n_z % prev == 0):
+            continue
+        done += 1
+        op, hid, hd, z, ctx = _setup(variant, n_z, hidden, [n_z, n_z], H, W, B, nl)
+        zo, ls, ld, hs = op.step_train(z, ctx)
+        th, thh = _torch_params(hid, hd)
+        zt = torch.from_numpy(z).double().requires_grad_(True)
+        ct = torch.from_numpy(ctx).double().requires_grad_(True) if ctx is not None else None
+        zn, lsd, ldt = OT.iaf_step(variant, zt, ct, th, thh, nl=nl)
+        g1, g2 = rng.randn(*z.shape).astype(np.float32), rng.randn(*z.shape).astype(np.float32)
+        g3 = rng.randn(B).astype(np.float32)
+        ((zn * torch.from_numpy(g1)).sum() + (lsd * torch.from_numpy(g2)).sum() + (ldt * torch.from_numpy(g3)).sum()).backward()
+        tag = (variant, n_z, hidden, H, W, B, nl)
+        assert _rel(zo, zn) < 1e-5 and _rel(ld, ldt) < 1e-5, tag
+        for res in (op.step_bwd(z, ctx, g1, g2, g3), op.step_bwd_saved(z, ctx, zo, ls, hs, g1, g2, g3)):
+            g_z, g_ctx, gw, gs, gb = res
+            assert _rel(g_z, zt.grad) < TOL, tag
+            if ctx is not None:
+                assert _rel(g_ctx, ct.grad) < TOL, tag
+            for i, l in enumerate(th + thh):
+                for g, k in zip((gw[i], gs[i], gb[i]), _keys(variant)):
+                    if float(l[k].grad.abs().max()) > 1e-9:
+                        assert _rel(g, l[k].grad) < TOL, (tag, i, k)
