@@ -39,6 +39,9 @@ SYMBOLS = {
     "iaf_step_fwd_train": (C.c_int, [_P, _P, _P, _P, _P, _P, C.POINTER(_P), C.c_int, _P]),
     "iaf_step_bwd_saved": (C.c_int, [_P, _P, _P, _P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), _P, _P, _P, _P, _P,
                                      C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.c_int, _P]),
+    "iaf_multiconv_fwd_train": (C.c_int, [_P, _P, _P, C.POINTER(_P), C.POINTER(_P), C.c_int, _P]),
+    "iaf_multiconv_bwd_saved": (C.c_int, [_P, _P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), _P, _P,
+                                          C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.c_int, _P]),
     "iaf_multiconv_bwd": (C.c_int, [_P, _P, _P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), _P, _P, C.POINTER(_P),
                                     C.POINTER(_P), C.POINTER(_P), C.c_int, _P]),
     "iaf_strerror": (C.c_char_p, [C.c_int]),

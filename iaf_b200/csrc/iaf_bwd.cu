@@ -792,7 +792,7 @@ int iaf_bwd_run(IafBwdPlan* pl, const IafBwdArgs* a, cudaStream_t stream, int* n
   auto ew_grid = [](size_t total) { return (int)std::min<size_t>(592, (total + BW_THREADS - 1) / BW_THREADS); };
 
   // activations: recomputed below, or the ones the training forward kept
-  const bool saved = a->have_saved && a->mode == IAF_MODE_STEP;
+  const bool saved = a->have_saved != 0;  // step: z', arw_logsd and the hidden activations; multiconv: the hidden activations
   const float* hcur[IAF_MAX_STAGES];
   for (int j = 1; j < nst; ++j) hcur[j] = saved ? a->h_saved[j - 1] : pl->h[j];
   hcur[0] = a->z;

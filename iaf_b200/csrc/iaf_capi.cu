@@ -466,6 +466,30 @@ int iaf_step_bwd_saved(iaf_plan_t* pl, const float* z, const float* z_out, const
                  g_scale, g_bias, B, (cudaStream_t)stream, z_out, logsd, hidden);
 }
 
+int iaf_multiconv_fwd_train(iaf_plan_t* pl, const float* z, const float* context, float* const* outs,
+                            float* const* hidden_out, int B, void* stream) {
+  if (!pl || !z || !outs || !outs[0]) return IAF_ERR_BAD_ARG;
+  if (pl->d.n_hidden > 0 && (!context || !hidden_out)) return IAF_ERR_BAD_ARG;
+  for (int j = 0; j < pl->d.n_hidden; ++j)
+    if (!hidden_out[j]) return IAF_ERR_BAD_ARG;
+  if (pl->d.n_heads == 2 && !outs[1]) return IAF_ERR_BAD_ARG;
+  return run(pl, IAF_MODE_MULTICONV, z, context, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, outs[0],
+             pl->d.n_heads == 2 ? outs[1] : nullptr, nullptr, nullptr, B, (cudaStream_t)stream, hidden_out);
+}
+
+int iaf_multiconv_bwd_saved(iaf_plan_t* pl, const float* z, const float* const* hidden, const float* const* w,
+                            const float* const* scale, const float* const* g_outs, float* g_z, float* g_context,
+                            float* const* g_w, float* const* g_scale, float* const* g_bias, int B, void* stream) {
+  if (!pl || !z || !g_outs || !g_outs[0] || !g_z) return IAF_ERR_BAD_ARG;
+  if (pl->d.n_hidden > 0 && !hidden) return IAF_ERR_BAD_ARG;
+  for (int j = 0; j < pl->d.n_hidden; ++j)
+    if (!hidden[j]) return IAF_ERR_BAD_ARG;
+  if (pl->d.n_heads == 2 && !g_outs[1]) return IAF_ERR_BAD_ARG;
+  // z_out_saved doubles as the "activations were kept" flag of run_bwd; the multiconv backward never reads it
+  return run_bwd(pl, IAF_MODE_MULTICONV, z, nullptr, w, scale, nullptr, nullptr, nullptr, g_outs, g_z, g_context, g_w,
+                 g_scale, g_bias, B, (cudaStream_t)stream, z, nullptr, hidden);
+}
+
 int iaf_multiconv_bwd(iaf_plan_t* pl, const float* z, const float* context, const float* const* w,
                       const float* const* scale, const float* const* g_outs, float* g_z, float* g_context,
                       float* const* g_w, float* const* g_scale, float* const* g_bias, int B, void* stream) {

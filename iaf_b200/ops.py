@@ -16,6 +16,7 @@ so the masked / normalised / packed weights are cached on the operator and re-pa
 when a parameter tensor changes.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -201,6 +202,18 @@ class IAFOperator(object):
                                               B, _stream(z.device)))
         return z_out, logsd, logdet
 
+    def _multiconv_train_raw(self, z, context):
+        """iaf_multiconv_fwd_train: the un-fused stack plus the hidden activations its backward needs."""
+        z, context, B, H, W = self._shapes(z, context)
+        plan = self._plan(H, W, z.device)
+        outs = [torch.empty((B, h, H, W), device=z.device, dtype=torch.float32) for h in self.heads]
+        hidden = [torch.empty((B, h, H, W), device=z.device, dtype=torch.float32) for h in self.hidden]
+        oarr = (C.c_void_p * len(outs))(*[o.data_ptr() for o in outs])
+        harr = (C.c_void_p * max(1, len(hidden)))(*[h.data_ptr() for h in hidden])
+        with torch.cuda.device(z.device):
+            _lib.check(self._lib.iaf_multiconv_fwd_train(plan, _ptr(z), _ptr(context), oarr, harr, B, _stream(z.device)))
+        return outs, hidden
+
     def _step_train_raw(self, z, context):
         """iaf_step_fwd_train: the step plus the hidden activations the backward needs (kept by the same kernels)."""
         z, context, B, H, W = self._shapes(z, context)
@@ -298,6 +311,13 @@ class IAFOperator(object):
                 g_outs = [torch.zeros((B, h, H, W), device=dev) if g is None else _check_input(g, "grad")
                           for g, h in zip(grads_out, self.heads)]
                 go = (C.c_void_p * len(g_outs))(*[g.data_ptr() for g in g_outs])
+                if saved is not None:
+                    hidden = saved[2]
+                    harr = (C.c_void_p * max(1, len(hidden)))(*[h.data_ptr() for h in hidden])
+                    _lib.check(self._lib.iaf_multiconv_bwd_saved(plan, _ptr(z), harr, arr([l[0] for l in layers]),
+                                                                 arr([l[1] for l in layers]), go, _ptr(g_z), _ptr(g_ctx),
+                                                                 pa(gw), pa(gs), pa(gb), B, _stream(dev)))
+                    return g_z, g_ctx, gw, gs, gb
                 _lib.check(self._lib.iaf_multiconv_bwd(plan, _ptr(z), _ptr(context), arr([l[0] for l in layers]),
                                                        arr([l[1] for l in layers]), go, _ptr(g_z), _ptr(g_ctx), pa(gw),
                                                        pa(gs), pa(gb), B, _stream(dev)))
@@ -352,14 +372,22 @@ class _StepFn(torch.autograd.Function):
 class _MulticonvFn(torch.autograd.Function):
     """autograd node of the un-fused operator: forward = iaf_multiconv_fwd, backward = iaf_multiconv_bwd."""
 
+    # IAF_MULTICONV_SAVED=1 (opt-in until confirmed on the GPU, tools/round2_first_call.sh): keep the hidden activations
+    # in the forward (iaf_multiconv_fwd_train) and skip the recompute in the backward (iaf_multiconv_bwd_saved), as the
+    # fused step's node already does.  Default: recompute (the path the round-1 GPU tests ran).
     @staticmethod
     def forward(ctx, op, z, context, *flat):
+        ctx.keep = os.environ.get("IAF_MULTICONV_SAVED", "0") == "1"
         with torch.no_grad():
-            outs = op._multiconv_raw(z, context)
+            if ctx.keep:
+                outs, hidden = op._multiconv_train_raw(z, context)
+            else:
+                outs, hidden = op._multiconv_raw(z, context), []
         ctx.op = op
         ctx.has_ctx = context is not None
+        ctx.n_hidden = len(hidden)
         ctx.set_materialize_grads(False)
-        ctx.save_for_backward(z, *([context] if context is not None else []), *flat)
+        ctx.save_for_backward(z, *([context] if context is not None else []), *hidden, *flat)
         return tuple(outs)
 
     @staticmethod
@@ -367,9 +395,12 @@ class _MulticonvFn(torch.autograd.Function):
         saved = ctx.saved_tensors
         z = saved[0]
         context = saved[1] if ctx.has_ctx else None
-        flat = saved[2 if ctx.has_ctx else 1:]
+        i = 2 if ctx.has_ctx else 1
+        hidden = list(saved[i:i + ctx.n_hidden])
+        flat = saved[i + ctx.n_hidden:]
         need_params = any(ctx.needs_input_grad[3:])
-        g_z, g_ctx, gw, gs, gb = ctx.op._backward("multiconv", z, context, _regroup(flat), g_outs, need_params)
+        g_z, g_ctx, gw, gs, gb = ctx.op._backward("multiconv", z, context, _regroup(flat), g_outs, need_params,
+                                                   saved=(None, None, hidden) if ctx.keep else None)
         return (None, g_z, g_ctx) + tuple(_flat_param_grads(gw, gs, gb, len(flat) // 3))
 
 

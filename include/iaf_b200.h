@@ -179,6 +179,15 @@ int iaf_step_bwd_saved(iaf_plan_t* plan, const float* z, const float* z_out, con
                        const float* g_logdet, float* g_z, float* g_context, float* const* g_w,
                        float* const* g_scale, float* const* g_bias, int B, void* stream);
 
+/* The same pair for the un-fused operator (the reference's own drop-in signatures train through it). */
+int iaf_multiconv_fwd_train(iaf_plan_t* plan, const float* z, const float* context,
+                            float* const* outs, float* const* hidden_out, int B, void* stream);
+int iaf_multiconv_bwd_saved(iaf_plan_t* plan, const float* z, const float* const* hidden,
+                            const float* const* w, const float* const* scale,
+                            const float* const* g_outs, float* g_z, float* g_context,
+                            float* const* g_w, float* const* g_scale, float* const* g_bias, int B,
+                            void* stream);
+
 /* Backward of the un-fused operator iaf_multiconv_fwd: g_outs[k] [B,head[k],H,W] is the
  * gradient at head k.  Same outputs as iaf_step_bwd. */
 int iaf_multiconv_bwd(iaf_plan_t* plan, const float* z, const float* context, const float* const* w,

@@ -126,6 +126,22 @@ class EmuOperator(object):
                                            _arr(gb) if params else None, B, None))
         return g_z, g_ctx, gw, gs, gb
 
+    def multiconv_train(self, z, ctx):
+        B = z.shape[0]
+        outs = [np.empty((B, h, self.H, self.W), np.float32) for h in self.heads]
+        hidden = [np.full((B, h, self.H, self.W), np.nan, np.float32) for h in self.hidden]
+        _check(self.lib.iaf_multiconv_fwd_train(self.plan, _p(z), _p(ctx), _arr(outs), _arr(hidden) if hidden else None, B, None))
+        return outs, hidden
+
+    def multiconv_bwd_saved(self, z, ctx_like, hidden, g_outs, params=True):
+        B = z.shape[0]
+        g_z, g_ctx, gw, gs, gb = self._grad_bufs(z, ctx_like, params)
+        _check(self.lib.iaf_multiconv_bwd_saved(self.plan, _p(z), _arr(hidden) if hidden else None,
+                                                _arr([l[0] for l in self.layers]), _arr([l[1] for l in self.layers]),
+                                                _arr(g_outs), _p(g_z), _p(g_ctx), _arr(gw) if params else None,
+                                                _arr(gs) if params else None, _arr(gb) if params else None, B, None))
+        return g_z, g_ctx, gw, gs, gb
+
     def multiconv_bwd(self, z, ctx, g_outs, params=True):
         B = z.shape[0]
         g_z, g_ctx, gw, gs, gb = self._grad_bufs(z, ctx, params)

@@ -139,11 +139,14 @@ def test_emulated_multiconv_backward(variant, heads):
     for o, r in zip(outs, ref):
         assert _rel(o, r) < 1e-5
     sum((r * torch.from_numpy(g)).sum() for r, g in zip(ref, g_outs)).backward()
-    g_z, g_ctx, gw, gs, gb = op.multiconv_bwd(z, ctx, g_outs)
-    assert _rel(g_z, zt.grad) < TOL and _rel(g_ctx, ct.grad) < TOL
-    for i, l in enumerate(th + thh):
-        for g, k in zip((gw[i], gs[i], gb[i]), _keys(variant)):
-            assert _rel(g, l[k].grad) < TOL, (i, k)
+    outs2, hs = op.multiconv_train(z, ctx)   # the training pair of the un-fused operator
+    assert all(np.array_equal(a, b) for a, b in zip(outs, outs2))
+    for res in (op.multiconv_bwd(z, ctx, g_outs), op.multiconv_bwd_saved(z, ctx, hs, g_outs)):
+        g_z, g_ctx, gw, gs, gb = res
+        assert _rel(g_z, zt.grad) < TOL and _rel(g_ctx, ct.grad) < TOL
+        for i, l in enumerate(th + thh):
+            for g, k in zip((gw[i], gs[i], gb[i]), _keys(variant)):
+                assert _rel(g, l[k].grad) < TOL, (i, k)
 
 
 def test_python_autograd_glue_over_the_emulated_abi(monkeypatch):
@@ -207,6 +210,15 @@ def test_python_autograd_glue_over_the_emulated_abi(monkeypatch):
     assert _rel(zg.grad.numpy(), zt.grad) < TOL
     assert _rel(dev[1][0].grad.numpy(), thh[0]["V"].grad) < TOL
     assert float(dev[2][0].grad.abs().max()) == 0.0   # head 1 received no gradient
+
+    # opt-in kept-activation path of the un-fused operator gives the same gradients
+    monkeypatch.setenv("IAF_MULTICONV_SAVED", "1")
+    ref_gz, ref_gv = zg.grad.clone(), dev[1][0].grad.clone()
+    for t in [zg, cg] + [t for l in dev for t in l]:
+        t.grad = None
+    op.multiconv(zg, cg)[0].sum().backward()
+    assert torch.allclose(zg.grad, ref_gz, rtol=1e-5, atol=1e-6) and torch.allclose(dev[1][0].grad, ref_gv, rtol=1e-5, atol=1e-6)
+    monkeypatch.delenv("IAF_MULTICONV_SAVED")
 
     # no grad requested: plain call, nothing recorded
     with torch.no_grad():

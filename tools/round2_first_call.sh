@@ -5,6 +5,9 @@
 set -u
 mkdir -p gpurun_out
 timeout 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 | tee gpurun_out/r2_gpu_tests.log
+# opt-in kept-activation path of the un-fused operator's autograd node (emulation-tested only so far)
+IAF_MULTICONV_SAVED=1 timeout 200 python -m pytest tests/test_gpu_backward.py -m gpu -q -k "multiconv or factory" 2>&1 | tail -1 | \
+  sed 's/^/[IAF_MULTICONV_SAVED=1] /' | tee -a gpurun_out/r2_ab.log
 build() {  # build <extra nvcc flags...>
   (cd iaf_b200/csrc && nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 "$@" -shared -Xcompiler -fPIC \
      -o ../lib/libiaf_b200.so iaf_capi.cu iaf_pack.cu iaf_simt.cu iaf_tc.cu iaf_bwd.cu 2>&1 | grep -E "error")
