@@ -39,6 +39,7 @@ SYMBOLS = {
     "iaf_step_fwd_train": (C.c_int, [_P, _P, _P, _P, _P, _P, C.POINTER(_P), C.c_int, _P]),
     "iaf_step_bwd_saved": (C.c_int, [_P, _P, _P, _P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), _P, _P, _P, _P, _P,
                                      C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.c_int, _P]),
+    "iaf_layer_bwd": (C.c_int, [_P] * 7 + [C.POINTER(_P), C.POINTER(_P)] + [_P] * 10 + [C.POINTER(_P)] * 3 + [C.c_int, _P]),
     "iaf_multiconv_fwd_train": (C.c_int, [_P, _P, _P, C.POINTER(_P), C.POINTER(_P), C.c_int, _P]),
     "iaf_multiconv_bwd_saved": (C.c_int, [_P, _P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), _P, _P,
                                           C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.c_int, _P]),

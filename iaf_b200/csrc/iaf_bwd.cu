@@ -322,6 +322,75 @@ __global__ void __launch_bounds__(BW_THREADS) iaf_bwd_affine_kernel(const __grid
   }
 }
 
+// fused layer (tf_train.py:56-85 / models.py:273-298), elementwise parts of its backward:
+//   pre:    z0 = post_mean + exp(post_logsd) * eps                                  (the sample the stack sees)
+//   affine: gkl = g_kl + g_kl_bc[b,c] + g_kl_cost[b];  d = z' - prior_mean;  E = exp(-2 prior_logsd)
+//           G_z' = g_z' + gkl d E,  G_logsd = gkl  ->  g_m, g_s, direct g_z0 as in the step;
+//           g_prior_mean = -gkl d E,  g_prior_logsd = gkl (1 - d^2 E)
+//   post:   g_post_mean = g_z0;  g_post_logsd = g_z0 exp(post_logsd) eps - gkl;  g_eps = g_z0 exp(post_logsd) - gkl eps
+struct IafLayerBwdParams {
+  const float* eps; const float* post_mean; const float* post_logsd; const float* prior_mean; const float* prior_logsd;
+  const float* g_zout; const float* g_kl; const float* g_kl_bc; const float* g_kl_cost;
+  float* z0; float* hb; float* g_z0;
+  float* g_post_mean; float* g_post_logsd; float* g_prior_mean; float* g_prior_logsd; float* g_eps;
+  int B, C, HW, cp, head_pad;
+  float scale;
+};
+__device__ __forceinline__ float bw_gkl(const IafLayerBwdParams& p, size_t e, int n, int c) {
+  float g = 0.f;
+  if (p.g_kl) g += __ldg(p.g_kl + e);
+  if (p.g_kl_bc) g += __ldg(p.g_kl_bc + (size_t)n * p.C + c);
+  if (p.g_kl_cost) g += __ldg(p.g_kl_cost + n);
+  return g;
+}
+__global__ void __launch_bounds__(BW_THREADS) iaf_bwd_layer_pre_kernel(const __grid_constant__ IafLayerBwdParams p) {
+  const size_t total = (size_t)p.B * p.C * p.HW;
+  for (size_t i = (size_t)blockIdx.x * BW_THREADS + threadIdx.x; i < total; i += (size_t)gridDim.x * BW_THREADS)
+    p.z0[i] = fmaf(expf(__ldg(p.post_logsd + i)), __ldg(p.eps + i), __ldg(p.post_mean + i));
+}
+__global__ void __launch_bounds__(BW_THREADS) iaf_bwd_layer_affine_kernel(const __grid_constant__ IafLayerBwdParams p) {
+  const size_t total = (size_t)p.B * p.head_pad * p.HW;
+  for (size_t i = (size_t)blockIdx.x * BW_THREADS + threadIdx.x; i < total; i += (size_t)gridDim.x * BW_THREADS) {
+    const int gp = (int)(i % p.HW);
+    const int c = (int)((i / p.HW) % p.head_pad);
+    const int n = (int)(i / ((size_t)p.HW * p.head_pad));
+    const int mcol = (c >> 2) * 8 + (c & 3), scol = mcol + 4;
+    const size_t om = ((size_t)n * p.cp + mcol) * p.HW + gp, os = ((size_t)n * p.cp + scol) * p.HW + gp;
+    if (c >= p.C) {
+      p.hb[om] = 0.f;
+      p.hb[os] = 0.f;
+      continue;
+    }
+    const size_t e = ((size_t)n * p.C + c) * p.HW + gp;
+    const float m = p.hb[om], s = p.hb[os];
+    const float ex = expf(-p.scale * s);
+    const float zn = (p.z0[e] - p.scale * m) * ex;
+    const float gkl = bw_gkl(p, e, n, c);
+    const float d = zn - __ldg(p.prior_mean + e);
+    const float E = expf(-2.0f * __ldg(p.prior_logsd + e));
+    float gzo = gkl * d * E;
+    if (p.g_zout) gzo += __ldg(p.g_zout + e);
+    p.g_prior_mean[e] = -gkl * d * E;
+    p.g_prior_logsd[e] = gkl * (1.0f - d * d * E);
+    p.hb[om] = -p.scale * ex * gzo;
+    p.hb[os] = -p.scale * zn * gzo + p.scale * gkl;
+    p.g_z0[e] = ex * gzo;
+  }
+}
+__global__ void __launch_bounds__(BW_THREADS) iaf_bwd_layer_post_kernel(const __grid_constant__ IafLayerBwdParams p) {
+  const size_t total = (size_t)p.B * p.C * p.HW;
+  for (size_t i = (size_t)blockIdx.x * BW_THREADS + threadIdx.x; i < total; i += (size_t)gridDim.x * BW_THREADS) {
+    const int c = (int)((i / p.HW) % p.C);
+    const int n = (int)(i / ((size_t)p.HW * p.C));
+    const float gkl = bw_gkl(p, i, n, c);
+    const float gz = p.g_z0[i];
+    const float sd = expf(__ldg(p.post_logsd + i)), ep = __ldg(p.eps + i);
+    p.g_post_mean[i] = gz;
+    p.g_post_logsd[i] = gz * sd * ep - gkl;
+    if (p.g_eps) p.g_eps[i] = gz * sd - gkl * ep;
+  }
+}
+
 // multiconv: the caller's head gradients -> packed column order; g_z starts at zero
 struct IafScatterParams {
   const float* g0; const float* g1;
@@ -642,6 +711,8 @@ struct IafBwdPlan {
   int scratch_B;
   float* h[IAF_MAX_STAGES];   // h[j] = input of stage j (j >= 1): [B][cout[j-1]][HW]
   float* hb;                  // heads raw / gradient: [B][ncol[last]][HW]
+  float* z0; float* gz0;      // fused-layer mode: the posterior sample and its gradient, [B][n_z][HW] (allocated on first use)
+  int z0_B;
   float* G[2];                // ping-pong gradient buffers of the hidden layers
   float* wT;                  // transposed weights of the current layer
   float* part;                // wgrad partials
@@ -658,6 +729,9 @@ static void bw_free_scratch(IafBwdPlan* pl) {
     pl->h[j] = nullptr;
   }
   if (pl->hb) cudaFree(pl->hb);
+  if (pl->z0) cudaFree(pl->z0);
+  if (pl->gz0) cudaFree(pl->gz0);
+  pl->z0 = pl->gz0 = nullptr; pl->z0_B = 0;
   if (pl->G[0]) cudaFree(pl->G[0]);
   if (pl->G[1]) cudaFree(pl->G[1]);
   if (pl->part) cudaFree(pl->part);
@@ -797,11 +871,40 @@ int iaf_bwd_run(IafBwdPlan* pl, const IafBwdArgs* a, cudaStream_t stream, int* n
   for (int j = 1; j < nst; ++j) hcur[j] = saved ? a->h_saved[j - 1] : pl->h[j];
   hcur[0] = a->z;
 
+  // fused-layer mode: the stack's input is the posterior sample z0 = post_mean + exp(post_logsd) * eps (a->z is eps), and
+  // the gradient of z0 is a workspace from which the gradients of the posterior statistics are formed at the end
+  const bool layer = a->mode == IAF_MODE_LAYER;
+  float* g_zin = a->g_z;
+  IafLayerBwdParams lq;
+  memset(&lq, 0, sizeof(lq));
+  if (layer) {
+    if (B > pl->z0_B) {
+      if (pl->z0) cudaFree(pl->z0);
+      if (pl->gz0) cudaFree(pl->gz0);
+      pl->z0 = pl->gz0 = nullptr; pl->z0_B = 0;
+      if (cudaMalloc(&pl->z0, sizeof(float) * B * d.n_z * HW) != cudaSuccess ||
+          cudaMalloc(&pl->gz0, sizeof(float) * B * d.n_z * HW) != cudaSuccess) return IAF_ERR_CUDA;
+      pl->z0_B = B;
+    }
+    lq.eps = a->z; lq.post_mean = a->post_mean; lq.post_logsd = a->post_logsd;
+    lq.prior_mean = a->prior_mean; lq.prior_logsd = a->prior_logsd;
+    lq.g_zout = a->g_zout; lq.g_kl = a->g_kl; lq.g_kl_bc = a->g_kl_bc; lq.g_kl_cost = a->g_kl_cost;
+    lq.z0 = pl->z0; lq.hb = pl->hb; lq.g_z0 = pl->gz0;
+    lq.g_post_mean = a->g_post_mean; lq.g_post_logsd = a->g_post_logsd;
+    lq.g_prior_mean = a->g_prior_mean; lq.g_prior_logsd = a->g_prior_logsd; lq.g_eps = a->g_eps;
+    lq.B = B; lq.C = d.n_z; lq.HW = HW; lq.cp = pl->ncol[last]; lq.head_pad = pl->head_pad; lq.scale = 0.1f;
+    IAF_LAUNCH(iaf_bwd_layer_pre_kernel, ew_grid((size_t)B * d.n_z * HW), BW_THREADS, 0, stream, lq);
+    if (cudaGetLastError() != cudaSuccess) return IAF_ERR_CUDA;
+    ++nl_;
+    hcur[0] = pl->z0;
+    g_zin = pl->gz0;
+  }
+
   // ---- 1. forward recompute, layer at a time ----
   for (int j = 0; j < nst && !saved; ++j) {
     IafLconvParams q;
     memset(&q, 0, sizeof(q));
-    q.in = j == 0 ? a->z : pl->h[j];
+    q.in = hcur[j];
     q.w = a->w_packed[j]; q.bias = a->bias_packed[j];
     q.padw = flip ? a->padw_packed[j] : nullptr;
     q.ctx = (j == 0 && j != last) ? a->ctx : nullptr;
@@ -816,7 +919,9 @@ int iaf_bwd_run(IafBwdPlan* pl, const IafBwdArgs* a, cudaStream_t stream, int* n
   }
 
   // ---- 2. gradient at the heads ----
-  if (a->mode == IAF_MODE_STEP) {
+  if (layer) {
+    IAF_LAUNCH(iaf_bwd_layer_affine_kernel, ew_grid((size_t)B * pl->head_pad * HW), BW_THREADS, 0, stream, lq);
+  } else if (a->mode == IAF_MODE_STEP) {
     IafAffineBwdParams q;
     memset(&q, 0, sizeof(q));
     q.z = a->z; q.g_zout = a->g_zout; q.g_logsd = a->g_logsd; q.g_logdet = a->g_logdet;
@@ -874,7 +979,7 @@ int iaf_bwd_run(IafBwdPlan* pl, const IafBwdArgs* a, cudaStream_t stream, int* n
     q.bwd = 1; q.nl = d.nl; q.flip = flip;
     float* Gnext = nullptr;
     if (j == 0) {
-      q.epi = EPI_BWD_Z; q.out = a->g_z;
+      q.epi = EPI_BWD_Z; q.out = g_zin;
     } else {
       q.epi = EPI_BWD_HIDDEN; q.hprev = hcur[j];
       Gnext = (j == 1 && a->g_ctx) ? a->g_ctx : pl->G[j & 1];  // the gradient at a_0 IS the context gradient
@@ -884,6 +989,12 @@ int iaf_bwd_run(IafBwdPlan* pl, const IafBwdArgs* a, cudaStream_t stream, int* n
     ++nl_;
     Gcur = Gnext;
     g_planes = pl->cin[j];
+  }
+
+  if (layer) {
+    IAF_LAUNCH(iaf_bwd_layer_post_kernel, ew_grid((size_t)B * d.n_z * HW), BW_THREADS, 0, stream, lq);
+    if (cudaGetLastError() != cudaSuccess) return IAF_ERR_CUDA;
+    ++nl_;
   }
 
   // ---- 4. raw-parameter gradients ----

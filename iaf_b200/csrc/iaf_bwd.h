@@ -9,7 +9,7 @@
 struct IafBwdPlan;
 
 struct IafBwdArgs {
-  int mode;  // IAF_MODE_STEP | IAF_MODE_MULTICONV
+  int mode;  // IAF_MODE_STEP | IAF_MODE_MULTICONV | IAF_MODE_LAYER
   int B;
   const float* z;
   const float* ctx;
@@ -30,6 +30,13 @@ struct IafBwdArgs {
   const float* z_out_saved;              // z'
   const float* logsd_saved;              // arw_logsd
   const float* h_saved[IAF_MAX_HIDDEN];  // h_{j+1} = output of hidden layer j
+  // fused-layer mode (IAF_MODE_LAYER): z is eps; the posterior / prior statistics and the KL gradients
+  const float* post_mean; const float* post_logsd; const float* prior_mean; const float* prior_logsd;
+  const float* g_kl;       // [B,C,H,W] or nullptr
+  const float* g_kl_bc;    // [B,C] or nullptr
+  const float* g_kl_cost;  // [B] or nullptr
+  float* g_post_mean; float* g_post_logsd; float* g_prior_mean; float* g_prior_logsd;
+  float* g_eps;            // nullable
   // results
   float* g_z;
   float* g_ctx;          // nullable

@@ -466,6 +466,49 @@ int iaf_step_bwd_saved(iaf_plan_t* pl, const float* z, const float* z_out, const
                  g_scale, g_bias, B, (cudaStream_t)stream, z_out, logsd, hidden);
 }
 
+int iaf_layer_bwd(iaf_plan_t* pl, const float* eps, const float* post_mean, const float* post_logsd,
+                  const float* prior_mean, const float* prior_logsd, const float* context, const float* const* w,
+                  const float* const* scale, const float* g_z_out, const float* g_kl, const float* g_kl_bc,
+                  const float* g_kl_cost, float* g_post_mean, float* g_post_logsd, float* g_prior_mean,
+                  float* g_prior_logsd, float* g_eps, float* g_context, float* const* g_w, float* const* g_scale,
+                  float* const* g_bias, int B, void* stream) {
+  if (!pl || !eps || !post_mean || !post_logsd || !prior_mean || !prior_logsd) return IAF_ERR_BAD_ARG;
+  if (!g_post_mean || !g_post_logsd || !g_prior_mean || !g_prior_logsd) return IAF_ERR_BAD_ARG;
+  if (pl->d.n_hidden > 0 && !context) return IAF_ERR_BAD_ARG;
+  if (pl->d.n_heads != 2 || pl->d.head[0] != pl->d.n_z) return IAF_ERR_BAD_SHAPE;
+  if (!pl->packed) return IAF_ERR_NOT_PACKED;
+  if (B <= 0) return IAF_ERR_BAD_ARG;
+  const iaf_desc_t& d = pl->d;
+  const bool want_params = g_w || g_scale || g_bias;
+  if (want_params) {
+    if (!w || !scale) return IAF_ERR_BAD_ARG;
+    for (int i = 0; i < d.n_hidden + d.n_heads; ++i)
+      if (!w[i] || !scale[i]) return IAF_ERR_BAD_ARG;
+  }
+  if (!pl->bwd) {
+    int st = iaf_bwd_plan_create(&pl->bwd, &d, pl->cin, pl->cout, pl->cout_pad, pl->head_pad);
+    if (st != IAF_OK) return st == IAF_ERR_CUDA ? cuda_fail(cudaGetLastError(), "iaf_bwd_plan_create") : st;
+  }
+  IafBwdArgs a;
+  memset(&a, 0, sizeof(a));
+  a.mode = IAF_MODE_LAYER; a.B = B; a.z = eps; a.ctx = context;
+  for (int j = 0; j < pl->n_stages; ++j) {
+    a.w_packed[j] = pl->w[j]; a.bias_packed[j] = pl->bias[j]; a.padw_packed[j] = pl->padw[j];
+  }
+  a.w_raw = w; a.scale_raw = scale;
+  a.post_mean = post_mean; a.post_logsd = post_logsd; a.prior_mean = prior_mean; a.prior_logsd = prior_logsd;
+  a.g_zout = g_z_out; a.g_kl = g_kl; a.g_kl_bc = g_kl_bc; a.g_kl_cost = g_kl_cost;
+  a.g_post_mean = g_post_mean; a.g_post_logsd = g_post_logsd; a.g_prior_mean = g_prior_mean; a.g_prior_logsd = g_prior_logsd;
+  a.g_eps = g_eps;
+  a.g_z = nullptr; a.g_ctx = d.n_hidden > 0 ? g_context : nullptr;
+  a.g_w = g_w; a.g_scale = g_scale; a.g_bias = g_bias;
+  int nl = 0;
+  int st = iaf_bwd_run(pl->bwd, &a, (cudaStream_t)stream, &nl);
+  if (st == IAF_ERR_CUDA) return cuda_fail(cudaGetLastError(), "iaf_bwd_run");
+  pl->launches += nl;
+  return st;
+}
+
 int iaf_multiconv_fwd_train(iaf_plan_t* pl, const float* z, const float* context, float* const* outs,
                             float* const* hidden_out, int B, void* stream) {
   if (!pl || !z || !outs || !outs[0]) return IAF_ERR_BAD_ARG;

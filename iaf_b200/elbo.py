@@ -180,10 +180,12 @@ class CudaIAFTrain(object):
     (SURVEY 8f-4).  ``obj.backward()`` on the result of forward() then yields the gradient of the training objective
     with respect to every parameter, the masked-AR ones included (masked taps get exactly zero, ar.py:369-373)."""
 
-    def __init__(self, params, hps, path="auto"):
+    def __init__(self, params, hps, path="auto", fused=False):
+        """fused=True: the whole block runs as ONE autograd node (iaf_layer_fwd / iaf_layer_bwd); needs
+        IAF_LAYER_AUTOGRAD=1 (opt-in until that node has had its first GPU run)."""
         from .ops import IAFOperator
         self.ops = {}
-        self.params, self.hps, self.path, self.IAFOperator = params, hps, path, IAFOperator
+        self.params, self.hps, self.path, self.IAFOperator, self.fused = params, hps, path, IAFOperator, fused
 
     def __call__(self, scope, eps, post_mean, post_logsd, prior_mean, prior_logsd, context):
         op = self.ops.get(scope)
@@ -194,6 +196,11 @@ class CudaIAFTrain(object):
         pre = scope + "/ar_multiconv2d/"
         op.set_weights([tuple(self.params[pre + n + "/" + k] for k in "Vgb")
                         for n in ("layer_0", "layer_1", "layer_out_0", "layer_out_1")])
+        if self.fused:
+            z, _, kl_bc, kl_cost = op.layer(eps, post_mean, post_logsd, prior_mean, prior_logsd, context, want_kl=False)
+            if not z.requires_grad:
+                raise RuntimeError("CudaIAFTrain(fused=True) needs IAF_LAYER_AUTOGRAD=1")
+            return z, kl_bc, kl_cost
         return stochastic_layer(lambda z, c: op.step(z, c, want_logdet=False)[:2], eps, post_mean, post_logsd, prior_mean,
                                 prior_logsd, context)
 

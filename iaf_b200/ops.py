@@ -258,7 +258,17 @@ class IAFOperator(object):
 
     def layer(self, eps, post_mean, post_logsd, prior_mean, prior_logsd, context, want_kl=True):
         """Fused posterior-sample -> IAF step -> KL block (tf_train.py:56-85, models.py:273-328).
-        Returns (z', kl [B,C,H,W] or None, kl_bc [B,C], kl_cost [B])."""
+        Returns (z', kl [B,C,H,W] or None, kl_bc [B,C], kl_cost [B]).  With IAF_LAYER_AUTOGRAD=1 (opt-in until its first
+        GPU run; the kernels are emulation-tested) the call is differentiable: backward = iaf_layer_bwd."""
+        if os.environ.get("IAF_LAYER_AUTOGRAD", "0") == "1" and self._needs_grad(eps, post_mean, post_logsd, prior_mean,
+                                                                                   prior_logsd, context):
+            flat = [t for l in self._layers for t in l]
+            z_out, kl, kl_bc, kl_cost = _LayerFn.apply(self, eps, post_mean, post_logsd, prior_mean, prior_logsd,
+                                                       context if self.hidden else None, *flat)
+            return z_out, (kl if want_kl else None), kl_bc, kl_cost
+        return self._layer_raw(eps, post_mean, post_logsd, prior_mean, prior_logsd, context, want_kl)
+
+    def _layer_raw(self, eps, post_mean, post_logsd, prior_mean, prior_logsd, context, want_kl=True):
         eps, context, B, H, W = self._shapes(eps, context)
         ts = [_check_input(t, n, eps.shape) for t, n in ((post_mean, "post_mean"), (post_logsd, "post_logsd"),
                                                           (prior_mean, "prior_mean"), (prior_logsd, "prior_logsd"))]
@@ -367,6 +377,51 @@ class _StepFn(torch.autograd.Function):
         g_z, g_ctx, gw, gs, gb = ctx.op._backward("step", z, context, _regroup(flat), (g_zout, g_logsd, g_logdet), need_params,
                                                    saved=(z_out, logsd, hidden))
         return (None, g_z, g_ctx) + tuple(_flat_param_grads(gw, gs, gb, len(flat) // 3))
+
+
+class _LayerFn(torch.autograd.Function):
+    """autograd node of the fused stochastic-layer block: forward = iaf_layer_fwd, backward = iaf_layer_bwd."""
+
+    @staticmethod
+    def forward(ctx, op, eps, post_mean, post_logsd, prior_mean, prior_logsd, context, *flat):
+        with torch.no_grad():
+            out = op._layer_raw(eps, post_mean, post_logsd, prior_mean, prior_logsd, context, True)
+        ctx.op = op
+        ctx.has_ctx = context is not None
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(eps, post_mean, post_logsd, prior_mean, prior_logsd, *([context] if context is not None else []),
+                              *flat)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_z, g_kl, g_kl_bc, g_kl_cost):
+        saved = ctx.saved_tensors
+        eps, pm, pls, prm, prl = saved[:5]
+        context = saved[5] if ctx.has_ctx else None
+        flat = saved[6 if ctx.has_ctx else 5:]
+        op = ctx.op
+        layers = _regroup(flat)
+        need_params = any(ctx.needs_input_grad[7:])
+        eps_c, context_c, B, H, W = op._shapes(eps, context)
+        dev = eps_c.device
+        plan = op._plan(H, W, dev, layers)
+        n = len(layers)
+        arr = lambda ts: (C.c_void_p * n)(*[t.data_ptr() for t in ts])
+        ts = [_check_input(t, "layer input", eps_c.shape) for t in (pm, pls, prm, prl)]
+        gs_in = [None if g is None else _check_input(g, "grad") for g in (g_z, g_kl, g_kl_bc, g_kl_cost)]
+        outs = [torch.empty_like(eps_c) for _ in range(5)]  # post_mean, post_logsd, prior_mean, prior_logsd, eps
+        g_ctx = torch.empty_like(context_c) if context_c is not None else None
+        gw = gs = gb = None
+        if need_params:
+            gw, gs, gb = ([torch.empty_like(l[j]) for l in layers] for j in range(3))
+        pa = lambda x: arr(x) if x is not None else None
+        with torch.cuda.device(dev):
+            _lib.check(op._lib.iaf_layer_bwd(plan, _ptr(eps_c), _ptr(ts[0]), _ptr(ts[1]), _ptr(ts[2]), _ptr(ts[3]),
+                                             _ptr(context_c), arr([l[0] for l in layers]), arr([l[1] for l in layers]),
+                                             _ptr(gs_in[0]), _ptr(gs_in[1]), _ptr(gs_in[2]), _ptr(gs_in[3]),
+                                             _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), _ptr(outs[3]), _ptr(outs[4]),
+                                             _ptr(g_ctx), pa(gw), pa(gs), pa(gb), B, _stream(dev)))
+        return (None, outs[4], outs[0], outs[1], outs[2], outs[3], g_ctx) + tuple(_flat_param_grads(gw, gs, gb, n))
 
 
 class _MulticonvFn(torch.autograd.Function):

@@ -188,6 +188,20 @@ int iaf_multiconv_bwd_saved(iaf_plan_t* plan, const float* z, const float* const
                             float* const* g_w, float* const* g_scale, float* const* g_bias, int B,
                             void* stream);
 
+/*
+ * Backward of the fused stochastic-layer block iaf_layer_fwd (tf_train.py:56-85 / models.py:273-298): upstream gradients
+ * of z_out (may be NULL), of the per-element kl (may be NULL), of kl_bc [B,n_z] (may be NULL) and of kl_cost [B] (may be
+ * NULL); results: the gradients of the posterior / prior statistics, of the noise (g_eps, may be NULL), of the context
+ * and of the raw parameters.  Activations are recomputed.
+ */
+int iaf_layer_bwd(iaf_plan_t* plan, const float* eps, const float* post_mean, const float* post_logsd,
+                  const float* prior_mean, const float* prior_logsd, const float* context,
+                  const float* const* w, const float* const* scale, const float* g_z_out,
+                  const float* g_kl, const float* g_kl_bc, const float* g_kl_cost, float* g_post_mean,
+                  float* g_post_logsd, float* g_prior_mean, float* g_prior_logsd, float* g_eps,
+                  float* g_context, float* const* g_w, float* const* g_scale, float* const* g_bias, int B,
+                  void* stream);
+
 /* Backward of the un-fused operator iaf_multiconv_fwd: g_outs[k] [B,head[k],H,W] is the
  * gradient at head k.  Same outputs as iaf_step_bwd. */
 int iaf_multiconv_bwd(iaf_plan_t* plan, const float* z, const float* context, const float* const* w,

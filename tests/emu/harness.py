@@ -89,6 +89,18 @@ class EmuOperator(object):
                                       _p(ctx), _p(zo), _p(kl), _p(kl_bc), _p(kl_cost), B, None))
         return zo, kl, kl_bc, kl_cost
 
+    def layer_bwd(self, eps, post_mean, post_logsd, prior_mean, prior_logsd, ctx, g_zout, g_kl, g_kl_bc, g_kl_cost,
+                  params=True):
+        B = eps.shape[0]
+        _, g_ctx, gw, gs, gb = self._grad_bufs(eps, ctx, params)
+        outs = [np.full_like(eps, np.nan) for _ in range(5)]  # g_post_mean, g_post_logsd, g_prior_mean, g_prior_logsd, g_eps
+        _check(self.lib.iaf_layer_bwd(self.plan, _p(eps), _p(post_mean), _p(post_logsd), _p(prior_mean), _p(prior_logsd),
+                                      _p(ctx), _arr([l[0] for l in self.layers]), _arr([l[1] for l in self.layers]),
+                                      _p(g_zout), _p(g_kl), _p(g_kl_bc), _p(g_kl_cost), _p(outs[0]), _p(outs[1]),
+                                      _p(outs[2]), _p(outs[3]), _p(outs[4]), _p(g_ctx), _arr(gw) if params else None,
+                                      _arr(gs) if params else None, _arr(gb) if params else None, B, None))
+        return outs, g_ctx, gw, gs, gb
+
     def _grad_bufs(self, z, ctx, params):
         g_z = np.full_like(z, np.nan)
         g_ctx = np.full_like(ctx, np.nan) if ctx is not None and self.hidden else None

@@ -185,7 +185,8 @@ def test_sharded_gradients_allreduce_equals_single_process_gloo_world2():
             np.testing.assert_allclose(g, params[k].grad.numpy(), rtol=1e-9, atol=1e-12)
 
 
-def test_tf_training_gradients_over_the_emulated_abi(monkeypatch):
+@pytest.mark.parametrize("fused", [False, True])
+def test_tf_training_gradients_over_the_emulated_abi(monkeypatch, fused):
     """CPU twin of test_training_objective_gradient_parity: elbo.CudaIAFTrain (autograd node -> iaf_step_fwd_train /
     iaf_step_bwd_saved) with the ctypes binding pointed at the host-emulated library (tests/emu), against fp64 autograd
     through the oracle block.  Test-only monkeypatching; the product refuses CPU tensors."""
@@ -213,7 +214,9 @@ def test_tf_training_gradients_over_the_emulated_abi(monkeypatch):
     for p in (p32, p64):
         for v in p.values():
             v.requires_grad_(True)
-    got = elbo.forward(p32, x, n32, elbo.CudaIAFTrain(p32, hps, path="simt"), hps)
+    if fused:   # the whole stochastic-layer block as one autograd node (iaf_layer_fwd / iaf_layer_bwd), opt-in
+        monkeypatch.setenv("IAF_LAYER_AUTOGRAD", "1")
+    got = elbo.forward(p32, x, n32, elbo.CudaIAFTrain(p32, hps, path="simt", fused=fused), hps)
     ref = elbo.forward(p64, x, n64, TorchIAF(p64, hps), hps)
     np.testing.assert_allclose(float(got["obj"].detach()), float(ref["obj"].detach()), rtol=2e-5)
     got["obj"].backward()

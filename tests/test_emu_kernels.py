@@ -220,6 +220,26 @@ def test_python_autograd_glue_over_the_emulated_abi(monkeypatch):
     assert torch.allclose(zg.grad, ref_gz, rtol=1e-5, atol=1e-6) and torch.allclose(dev[1][0].grad, ref_gv, rtol=1e-5, atol=1e-6)
     monkeypatch.delenv("IAF_MULTICONV_SAVED")
 
+    # opt-in autograd node of the fused layer block (iaf_layer_fwd / iaf_layer_bwd) against the same block built from
+    # torch ops around the differentiable step
+    from iaf_b200.elbo import stochastic_layer
+    monkeypatch.setenv("IAF_LAYER_AUTOGRAD", "1")
+    g = torch.Generator().manual_seed(4)
+    mk = lambda s_=1.0: (s_ * torch.randn(z.shape, generator=g)).requires_grad_(True)
+    eps_t, pm, pls, prm, prl = torch.randn(z.shape, generator=g), mk(), mk(0.3), mk(), mk(0.3)
+    for t in [cg] + [t for l in dev for t in l]:
+        t.grad = None
+    z1, _, kl_bc, kl_cost = op.layer(eps_t, pm, pls, prm, prl, cg, want_kl=False)
+    (z1.square().sum() + torch.clamp(kl_bc.mean(dim=0), min=0.25).sum() + 0.5 * kl_cost.sum()).backward()
+    got = [t.grad.clone() for t in (pm, pls, prm, prl, cg, dev[0][0], dev[2][1])]
+    for t in [pm, pls, prm, prl, cg] + [t for l in dev for t in l]:
+        t.grad = None
+    z2, bc2, cost2 = stochastic_layer(lambda a, b: op.step(a, b, want_logdet=False)[:2], eps_t, pm, pls, prm, prl, cg)
+    (z2.square().sum() + torch.clamp(bc2.mean(dim=0), min=0.25).sum() + 0.5 * cost2.sum()).backward()
+    for a, t in zip(got, (pm, pls, prm, prl, cg, dev[0][0], dev[2][1])):
+        assert float((a - t.grad).abs().max()) <= 2e-5 * max(float(t.grad.abs().max()), 1e-6)
+    monkeypatch.delenv("IAF_LAYER_AUTOGRAD")
+
     # no grad requested: plain call, nothing recorded
     with torch.no_grad():
         assert not op.step(zg, cg)[0].requires_grad
@@ -309,3 +329,59 @@ def test_emulated_random_shapes_forward_and_both_backward_paths():
                 for g, k in zip((gw[i], gs[i], gb[i]), _keys(variant)):
                     if float(l[k].grad.abs().max()) > 1e-9:
                         assert _rel(g, l[k].grad) < TOL, (tag, i, k)
+
+
+@pytest.mark.parametrize("variant,n_z,hidden,H,W,B,nl,which", [
+    ("tf", 4, [8, 8], 6, 6, 3, "elu", "all"),          # IAFLayer.down's shape family (tf_train.py:69: two hidden layers)
+    ("theano", 4, [8], 5, 7, 2, "softplus", "all"),    # cvae_layer down_q (models.py:273-298)
+    ("tf", 6, [12], 3, 5, 2, "elu", "bc_only"),        # only the free-bits input (kl_bc) carries a gradient
+    ("theano", 4, [], 4, 4, 2, "elu", "z_only"),       # depth_ar = 0, only z' used downstream
+])
+def test_emulated_fused_layer_backward(variant, n_z, hidden, H, W, B, nl, which):
+    """iaf_layer_bwd (the elementwise pre / affine / post kernels around the stack's backward) against fp64 autograd
+    through the restated block: posterior sample, logqs, the step, prior logps, kl and its two reductions."""
+    import math
+    op, hid, hd, _, _ = _setup(variant, n_z, hidden, [n_z, n_z], H, W, B, nl)
+    rng = np.random.RandomState(11)
+    shp = (B, n_z, H, W)
+    eps, pm, prm = (rng.randn(*shp).astype(np.float32) for _ in range(3))
+    pls, prl = (0.3 * rng.randn(*shp).astype(np.float32) for _ in range(2))
+    ctx = (0.1 * rng.randn(B, hidden[0], H, W)).astype(np.float32) if hidden else None
+    g_z = rng.randn(*shp).astype(np.float32) if which in ("all", "z_only") else None
+    g_kl = rng.randn(*shp).astype(np.float32) if which == "all" else None
+    g_bc = rng.randn(B, n_z).astype(np.float32) if which in ("all", "bc_only") else None
+    g_cost = rng.randn(B).astype(np.float32) if which == "all" else None
+    # forward agrees with the block first
+    zo, kl, kl_bc, kl_cost = op.layer(eps, pm, pls, prm, prl, ctx if ctx is not None else np.zeros((B, 1, H, W), np.float32))
+    th, thh = _torch_params(hid, hd)
+    t = lambda a: torch.from_numpy(a).double().requires_grad_(True)
+    te, tpm, tpls, tprm, tprl = t(eps), t(pm), t(pls), t(prm), t(prl)
+    tc = t(ctx) if ctx is not None else None
+    c = 0.5 * math.log(2.0 * math.pi)
+    z0 = tpm + torch.exp(tpls) * te
+    zn, lsd, _ = OT.iaf_step(variant, z0, tc, th, thh, nl=nl)
+    klt = (-c - tpls - 0.5 * te * te + lsd) - (-c - tprl - 0.5 * (zn - tprm) ** 2 * torch.exp(-2.0 * tprl))
+    assert _rel(zo, zn) < 1e-5 and _rel(kl, klt) < 1e-5 and _rel(kl_cost, klt.sum(dim=(1, 2, 3))) < 1e-5
+    loss = 0.0
+    if g_z is not None:
+        loss = loss + (zn * torch.from_numpy(g_z)).sum()
+    if g_kl is not None:
+        loss = loss + (klt * torch.from_numpy(g_kl)).sum()
+    if g_bc is not None:
+        loss = loss + (klt.sum(dim=(2, 3)) * torch.from_numpy(g_bc)).sum()
+    if g_cost is not None:
+        loss = loss + (klt.sum(dim=(1, 2, 3)) * torch.from_numpy(g_cost)).sum()
+    loss.backward()
+    outs, g_ctx, gw, gs, gb = op.layer_bwd(eps, pm, pls, prm, prl, ctx, g_z, g_kl, g_bc, g_cost)
+    for got, ref, name in zip(outs, (tpm, tpls, tprm, tprl, te), ("post_mean", "post_logsd", "prior_mean", "prior_logsd", "eps")):
+        r = ref.grad if ref.grad is not None else torch.zeros_like(ref)
+        if float(r.abs().max()) > 1e-12:
+            assert _rel(got, r) < TOL, name
+        else:
+            assert float(np.abs(got).max()) < 1e-12, name
+    if ctx is not None:
+        assert _rel(g_ctx, tc.grad) < TOL
+    for i, l in enumerate(th + thh):
+        for g, k in zip((gw[i], gs[i], gb[i]), _keys(variant)):
+            if float(l[k].grad.abs().max()) > 1e-9:
+                assert _rel(g, l[k].grad) < TOL, (i, k)

@@ -8,6 +8,22 @@ timeout 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 | tee gpurun_out/
 # opt-in kept-activation path of the un-fused operator's autograd node (emulation-tested only so far)
 IAF_MULTICONV_SAVED=1 timeout 200 python -m pytest tests/test_gpu_backward.py -m gpu -q -k "multiconv or factory" 2>&1 | tail -1 | \
   sed 's/^/[IAF_MULTICONV_SAVED=1] /' | tee -a gpurun_out/r2_ab.log
+# opt-in autograd node of the fused layer block (iaf_layer_bwd: emulation-tested only so far)
+IAF_LAYER_AUTOGRAD=1 timeout 200 python - <<'PY' 2>&1 | tail -2 | sed 's/^/[IAF_LAYER_AUTOGRAD=1] /' | tee -a gpurun_out/r2_ab.log
+import numpy as np, torch, sys
+sys.path.insert(0, ".")
+from iaf_b200 import elbo
+from tests.test_elbo import _setup
+from oracle.elbo_oracle import TorchIAF
+hps = dict(z_size=32, h_size=64, depth=2, num_blocks=1, kl_min=0.25, image_size=32)
+pg, xg, ng = _setup(hps, 3, 9, torch.float32, "cuda"); pc, xc, nc = _setup(hps, 3, 9, torch.float64, "cpu")
+for p in (pg, pc):
+    for v in p.values(): v.requires_grad_(True)
+got = elbo.forward(pg, xg, ng, elbo.CudaIAFTrain(pg, hps, fused=True), hps); ref = elbo.forward(pc, xc, nc, TorchIAF(pc, hps), hps)
+got["obj"].backward(); ref["obj"].backward()
+worst = max(float((pg[k].grad.double().cpu() - pc[k].grad).abs().max()) / max(float(pc[k].grad.abs().max()), 1e-12) for k in pc if pc[k].grad is not None)
+print("fused-layer training gradients: worst relative error %.2e (expect < 2e-3)" % worst)
+PY
 build() {  # build <extra nvcc flags...>
   (cd iaf_b200/csrc && nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 "$@" -shared -Xcompiler -fPIC \
      -o ../lib/libiaf_b200.so iaf_capi.cu iaf_pack.cu iaf_simt.cu iaf_tc.cu iaf_bwd.cu 2>&1 | grep -E "error")
