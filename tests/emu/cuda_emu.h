@@ -19,6 +19,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <thread>
 #include <vector>
 #include <algorithm>
@@ -46,7 +47,7 @@ namespace emu {
 inline thread_local uint3 t_threadIdx, t_blockIdx;
 inline dim3 g_blockDim, g_gridDim;
 inline unsigned char* g_dyn_smem = nullptr;
-inline std::barrier<>* g_bar = nullptr;
+inline thread_local std::barrier<>* t_bar = nullptr;
 }  // namespace emu
 #define threadIdx (emu::t_threadIdx)
 #define blockIdx (emu::t_blockIdx)
@@ -59,7 +60,7 @@ static inline void iaf_cp_async4(float* dst, const float* src, bool valid) { *ds
 static inline void iaf_cp_async_commit() {}
 template <int N> static inline void iaf_cp_async_wait() {}
 
-static inline void __syncthreads() { emu::g_bar->arrive_and_wait(); }
+static inline void __syncthreads() { emu::t_bar->arrive_and_wait(); }
 static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { return std::atomic_ref<unsigned>(*p).fetch_add(v); }
 static inline float atomicAdd(float* p, float v) { return std::atomic_ref<float>(*p).fetch_add(v); }
@@ -104,32 +105,37 @@ static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cu
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
 
 namespace emu {
-// run one grid: blocks one after another, the threads of a block as std::threads sharing a barrier
+// run one grid: blocks one after another (static / dynamic shared memory is one CTA's at a time), the threads of a block as
+// std::threads.  The threads are created once per launch and walk the blocks together: a fresh barrier per block serves
+// __syncthreads (a thread that returns early drops out of it, as on the device), a second reusable one marks the block
+// boundary.
 template <class K, class... A>
 inline void launch(K kernel, dim3 grid, dim3 block, size_t smem, const A&... args) {
   g_blockDim = block;
   g_gridDim = grid;
   const unsigned nthreads = block.x * block.y * block.z;
+  const size_t nblocks = (size_t)grid.x * grid.y * grid.z;
   std::vector<unsigned char> dyn(smem + 256);
   g_dyn_smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(dyn.data()) + 255) / 256 * 256);
-  for (unsigned bz = 0; bz < grid.z; ++bz)
-    for (unsigned by = 0; by < grid.y; ++by)
-      for (unsigned bx = 0; bx < grid.x; ++bx) {
-        std::barrier<> bar((std::ptrdiff_t)nthreads);
-        g_bar = &bar;
-        std::vector<std::thread> th;
-        th.reserve(nthreads);
-        for (unsigned t = 0; t < nthreads; ++t) {
-          th.emplace_back([&, t]() {
-            t_threadIdx = uint3{t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
-            t_blockIdx = uint3{bx, by, bz};
-            kernel(args...);
-            bar.arrive_and_drop();  // an exited thread no longer takes part in __syncthreads
-          });
-        }
-        for (auto& x : th) x.join();
+  std::vector<std::unique_ptr<std::barrier<>>> bars;
+  bars.reserve(nblocks);
+  for (size_t b = 0; b < nblocks; ++b) bars.emplace_back(new std::barrier<>((std::ptrdiff_t)nthreads));
+  std::barrier<> boundary((std::ptrdiff_t)nthreads);
+  std::vector<std::thread> th;
+  th.reserve(nthreads);
+  for (unsigned t = 0; t < nthreads; ++t) {
+    th.emplace_back([&, t]() {
+      t_threadIdx = uint3{t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
+      for (size_t b = 0; b < nblocks; ++b) {
+        t_blockIdx = uint3{(unsigned)(b % grid.x), (unsigned)((b / grid.x) % grid.y), (unsigned)(b / ((size_t)grid.x * grid.y))};
+        t_bar = bars[b].get();
+        kernel(args...);
+        bars[b]->arrive_and_drop();  // an exited thread no longer takes part in this block's __syncthreads
+        boundary.arrive_and_wait();  // nobody enters the next block while this one still uses the shared memory
       }
-  g_bar = nullptr;
+    });
+  }
+  for (auto& x : th) x.join();
 }
 }  // namespace emu
 #define IAF_LAUNCH(kernel, grid, block, smem, stream, ...) emu::launch(kernel, dim3(grid), dim3(block), (size_t)(smem), __VA_ARGS__)
