@@ -23,6 +23,9 @@
 #include <thread>
 #include <vector>
 #include <algorithm>
+#if defined(__SANITIZE_ADDRESS__)
+#include <sanitizer/asan_interface.h>
+#endif
 
 #define __global__
 #define __device__
@@ -115,8 +118,17 @@ inline void launch(K kernel, dim3 grid, dim3 block, size_t smem, const A&... arg
   g_gridDim = grid;
   const unsigned nthreads = block.x * block.y * block.z;
   const size_t nblocks = (size_t)grid.x * grid.y * grid.z;
-  std::vector<unsigned char> dyn(smem + 256);
+  std::vector<unsigned char> dyn(smem + 512);
   g_dyn_smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(dyn.data()) + 255) / 256 * 256);
+#if defined(__SANITIZE_ADDRESS__)
+  // under AddressSanitizer the bytes past the requested dynamic shared memory are poisoned: an out-of-range smem index
+  // in a kernel is reported instead of landing in the allocation's slack
+  ASAN_POISON_MEMORY_REGION(g_dyn_smem + smem, (size_t)(dyn.data() + dyn.size() - (g_dyn_smem + smem)));
+  struct Unpoison {
+    void* p; size_t n;
+    ~Unpoison() { ASAN_UNPOISON_MEMORY_REGION(p, n); }
+  } unpoison{g_dyn_smem + smem, (size_t)(dyn.data() + dyn.size() - (g_dyn_smem + smem))};
+#endif
   std::vector<std::unique_ptr<std::barrier<>>> bars;
   bars.reserve(nblocks);
   for (size_t b = 0; b < nblocks; ++b) bars.emplace_back(new std::barrier<>((std::ptrdiff_t)nthreads));
