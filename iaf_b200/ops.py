@@ -53,7 +53,13 @@ class IAFOperator(object):
              reference's layouts: tf V [3,3,Cin,Cout], g, b; theano w [Cout,Cin+1,3,3], s, b.
     """
 
-    def __init__(self, variant, n_z, hidden, heads, nl="elu", path="auto"):
+    def __init__(self, variant, n_z, hidden, heads, nl="elu", path="auto", checknan=None):
+        """checknan="raise": the reference driver's NaN guard (graphy/function.py:107-110 raises "NaN detected" when the sum
+        of a minibatch's outputs is NaN; train.py:211, tf_train.py:283-285 stop likewise): after a step, the per-sample
+        logdet (a sum over every element the kernel produced) is checked on the host.  Off by default: it synchronises."""
+        if checknan not in (None, "raise"):
+            raise ValueError("checknan must be None or 'raise'")
+        self.checknan = checknan
         if variant not in _lib.VARIANTS:
             raise ValueError("variant must be 'tf' or 'theano'")
         if nl not in _lib.NLS:
@@ -188,8 +194,15 @@ class IAFOperator(object):
         if self._needs_grad(z, context):
             flat = [t for l in self._layers for t in l]
             z_out, logsd, logdet = _StepFn.apply(self, z, context if self.hidden else None, *flat)
+            self._nan_guard(logdet)
             return z_out, (logsd if want_logsd else None), (logdet if want_logdet else None)
-        return self._step_raw(z, context, want_logsd, want_logdet)
+        out = self._step_raw(z, context, want_logsd, want_logdet or self.checknan == "raise")
+        self._nan_guard(out[2])
+        return out[0], out[1], (out[2] if want_logdet else None)
+
+    def _nan_guard(self, logdet):
+        if self.checknan == "raise" and bool(torch.isnan(logdet.detach().sum())):
+            raise FloatingPointError("NaN detected")  # graphy/function.py:110
 
     def _step_raw(self, z, context, want_logsd=True, want_logdet=True):
         z, context, B, H, W = self._shapes(z, context)

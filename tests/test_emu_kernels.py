@@ -240,6 +240,14 @@ def test_python_autograd_glue_over_the_emulated_abi(monkeypatch):
         assert float((a - t.grad).abs().max()) <= 2e-5 * max(float(t.grad.abs().max()), 1e-6)
     monkeypatch.delenv("IAF_LAYER_AUTOGRAD")
 
+    # the reference driver's NaN guard (graphy/function.py:107-110), opt-in
+    opn = ops.IAFOperator(variant, n_z, hidden, [n_z, n_z], nl="elu", path="simt", checknan="raise").set_weights(frozen)
+    opn.step(torch.from_numpy(z), torch.from_numpy(ctx))
+    zbad = torch.from_numpy(z).clone()
+    zbad[1, 0, 0, 0] = float("nan")
+    with pytest.raises(FloatingPointError):
+        opn.step(zbad, torch.from_numpy(ctx), want_logdet=False)
+
     # no grad requested: plain call, nothing recorded
     with torch.no_grad():
         assert not op.step(zg, cg)[0].requires_grad
