@@ -48,3 +48,6 @@ timeout 200 python -m pytest tests/test_gpu_backward.py -m gpu -x -q 2>&1 | tail
 build   # back to the default build
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:'iaf_lconv|iaf_bwd_wgrad' -s 30 -c 5 -f \
   -o gpurun_out/r2_bwd_c2a python tools/bench_bwd.py c2a 1 > gpurun_out/r2_ncu_bwd.log 2>&1
+# memory / shared-memory hazard checks of the real kernels on one small case each (compute-sanitizer is in the image)
+timeout 240 compute-sanitizer --tool memcheck --error-exitcode 3 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "test_step_against_fp64_oracle and tf-64-16x16" 2>&1 | tail -3 | sed 's/^/[memcheck] /' | tee -a gpurun_out/r2_ab.log
+timeout 240 compute-sanitizer --tool racecheck --error-exitcode 3 python -m pytest tests/test_gpu_backward.py -m gpu -x -q -k "tf-8x8-5x7 or 16x16-5x7" 2>&1 | tail -3 | sed 's/^/[racecheck] /' | tee -a gpurun_out/r2_ab.log
