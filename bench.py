@@ -1,33 +1,39 @@
 #!/usr/bin/env python
 """bench.py -- IAF-transform throughput on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2a|c2b]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2a|c2b|...]
 
 A "step" is one fused IAF step (masked-AR conv stack -> mu, s -> z' = (z - .1 mu)/exp(.1 s),
-per-element arw_logsd, per-sample logdet) over one batch of 256 synthetic samples of
-n_z=32, 16x16.  Metric: latent elements/s = B*n_z*H*W / t_step, whole job.
+per-element arw_logsd, per-sample logdet) over one GLOBAL batch of 256 synthetic samples of
+n_z=32, 16x16.  Metric: latent elements/s = 256*n_z*H*W / t_step, whole job.
 
-* value      : inputs resident in HBM, K steps timed with CUDA events (one CUDA graph of K
-               launches, or K direct launches), max over ranks.  The K steps rotate through
-               NSETS input/output sets whose footprint exceeds L2, so no step finds its
-               inputs in L2.
+* value      : inputs resident in HBM.  The K steps are grouped into ELBO evaluations of E steps
+               (E = the number of IAF steps per ELBO of the model the workload comes from); each group
+               is one CUDA-graph replay followed by the ELBO scalar (sum of the group's log-dets) and,
+               at N > 1, ONE all-reduce of that scalar (tf_train.py:142), issued on a side stream so it
+               overlaps the next group's kernels.  CUDA events around the whole region, max over ranks.
+               The steps rotate through NSETS input/output sets whose footprint exceeds L2.
+* roofline   : the step kernel(s) alone: one CUDA graph of K back-to-back launches, CUDA events;
+               bound = whichever of algorithmic-bytes/HBM-peak and algorithmic-flops/bf16-peak is larger.
 * e2e        : same metric through the public host-buffer entry (IAFOperator.submit_host ->
                iaf_step_submit_host): pinned host inputs H2D, step, results D2H, every step,
                pipelined over three device staging slots; timed until wait_host() returns.
-* roofline   : the step kernel against the measured HBM (or bf16 tensor) peak.
-* cpu_baseline: the oracle's torch-CPU port of the reference path on this box's cores,
-               on a bounded sample of the same workload (rank 0, N=1).
-* --impl reference: times that CPU port instead (the reference's Theano/TF code cannot
-               run in this image), same JSON shape.
+* also       : the other headline shape (hidden [160,160]: c2b at N=1, the same batch sharded = c5 at N>1),
+               device-timed in the same run.
+* cpu_baseline / --impl reference: the oracle's torch-CPU port of the reference path on this box's
+               cores (the reference's Theano/TF code cannot run in this image).  ONE routine
+               serves both: per thread-count candidate 3 warm-up + 5 timed calls (median), the best
+               candidate then runs the timed steps; the b200 arm runs it in a fresh subprocess so that
+               both arms measure under the same conditions.
 
-N>1: launched by torchrun, one rank per GPU; the batch dimension is sharded (every rank
-owns 256 samples: weak scaling), the only collective is one NCCL all-reduce of the scalar
-sum of log-dets (the ELBO term) at the end of the timed region (tf_train.py:142).
+N>1: launched by torchrun, one rank per GPU; the GLOBAL batch of 256 is sharded (256/N samples per rank:
+strong scaling, north_star / SURVEY 8e), weights replicated, no data-path collective.
 """
 import argparse
 import json
 import os
 import statistics
+import subprocess
 import sys
 import threading
 import time
@@ -36,19 +42,20 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-import numpy as np  # noqa: E402
+import numpy as np  # noqa: E402,F401
 import torch  # noqa: E402
 
+GLOBAL_B = 256
 WORKLOADS = {
-    # name: (variant, n_z, hidden, H, W, B, roofline bound)
-    "c2a": ("tf", 32, [64], 16, 16, 256, "hbm"),
-    "c2b": ("tf", 32, [160, 160], 16, 16, 256, "tensor"),
+    # name: (variant, n_z, hidden, H, W, global batch, IAF steps per ELBO evaluation of the model it comes from)
+    "c2a": ("tf", 32, [64], 16, 16, GLOBAL_B, 6),               # hidden [64]: README cifar10 model, depths [2,2,2] -> 6 steps/ELBO
+    "c2b": ("tf", 32, [160, 160], 16, 16, GLOBAL_B, 20),        # hidden [160,160]: tf_train.py, num_blocks=20 x depth=1
     # per-step shapes of the other BASELINE configs (parity-test cases; benched for the record, not the headline)
-    "c1": ("theano", 32, [64], 16, 16, 16, "hbm"),              # README example, batch 16, level 0
-    "c1_l1": ("theano", 32, [64], 8, 8, 16, "hbm"),             # ... level 1
-    "c1_l2": ("theano", 32, [64], 4, 4, 16, "hbm"),             # ... level 2
-    "c3": ("tf", 32, [160, 160], 16, 16, 32, "tensor"),         # tf_train.py default per-GPU batch
-    "c4_l1": ("theano", 32, [160, 160], 8, 8, 16, "tensor"),    # Table-3 config, second level
+    "c1": ("theano", 32, [64], 16, 16, 16, 6),                  # README example, batch 16, level 0
+    "c1_l1": ("theano", 32, [64], 8, 8, 16, 6),                 # ... level 1
+    "c1_l2": ("theano", 32, [64], 4, 4, 16, 6),                 # ... level 2
+    "c3": ("tf", 32, [160, 160], 16, 16, 32, 20),               # tf_train.py default per-GPU batch
+    "c4_l1": ("theano", 32, [160, 160], 8, 8, 16, 20),          # Table-3 config, second level
 }
 METRIC = "IAF latents/sec (z',logdet) @ n_z=32,16x16,bs256"
 UNIT = "latent elements/s"
@@ -59,8 +66,66 @@ def measured_peaks():
     if os.path.exists(p):
         with open(p) as f:
             d = json.load(f)
-        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), "measured (MEASURED_PEAKS.json)"
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), "measured (MEASURED_PEAKS.json, burst)"
     return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------------
+# host topology: physical cores, NUMA nodes, the GPU's local CPUs
+# ----------------------------------------------------------------------------------------------
+def _parse_cpulist(s):
+    out = set()
+    for part in s.strip().split(","):
+        if not part:
+            continue
+        if "-" in part:
+            a, b = part.split("-")
+            out.update(range(int(a), int(b) + 1))
+        else:
+            out.add(int(part))
+    return out
+
+
+def host_topology():
+    """(allowed cpus, physical cores among them, physical cores of the largest NUMA node among them)."""
+    allowed = set(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else set(range(os.cpu_count() or 1))
+    phys = set()
+    for c in sorted(allowed):
+        try:
+            with open("/sys/devices/system/cpu/cpu%d/topology/thread_siblings_list" % c) as f:
+                sib = _parse_cpulist(f.read())
+            phys.add(min(sib & allowed) if sib & allowed else c)
+        except OSError:
+            phys.add(c)
+    node_phys = 0
+    try:
+        for n in os.listdir("/sys/devices/system/node"):
+            if n.startswith("node") and n[4:].isdigit():
+                with open("/sys/devices/system/node/%s/cpulist" % n) as f:
+                    node_phys = max(node_phys, len(_parse_cpulist(f.read()) & phys))
+    except OSError:
+        pass
+    return allowed, len(phys), node_phys or len(phys)
+
+
+def bind_to_gpu_numa(index):
+    """Pin this process (and therefore the pinned host buffers it allocates afterwards) to the CPUs NVML reports as
+    local to GPU ``index``.  Returns a short description for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {w * 64 + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        allowed = set(os.sched_getaffinity(0))
+        cpus &= allowed
+        if cpus and cpus != allowed:
+            os.sched_setaffinity(0, cpus)
+            return "bound to %d CPUs local to GPU %d (NVML cpu affinity)" % (len(cpus), index)
+        return "GPU %d is local to every allowed CPU (%d): no binding needed" % (index, len(allowed))
+    except Exception as e:  # pragma: no cover
+        return "not bound (%s)" % type(e).__name__
 
 
 class ClockSampler(object):
@@ -109,10 +174,10 @@ class ClockSampler(object):
                  0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
                  0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
         timed = [s for s in self.samples if s[0] == "timed"]
-        window = "timed region"
+        window = "timed regions"
         if len(timed) < 3:
             timed = [s for s in self.samples if s[0] in ("timed", "e2e", "warmup")]
-            window = "warmup+timed+e2e (timed region shorter than 3 samples)"
+            window = "warmup+timed+e2e (timed regions shorter than 3 samples)"
         if not timed:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "no samples"}
         bits = 0
@@ -123,9 +188,9 @@ class ClockSampler(object):
                 "samples": len(timed), "window": window}
 
 
-def workload_string(name):
-    variant, n_z, hidden, H, W, B, _ = WORKLOADS[name]
-    return "%s: single IAF step, n_z=%d hidden=%s %dx%d batch %d per GPU, %s-variant numerics" % (
+def workload_string(name, world=1):
+    variant, n_z, hidden, H, W, B, E = WORKLOADS[name]
+    return "%s: single IAF step, n_z=%d hidden=%s %dx%d global batch %d, %s-variant numerics" % (
         name, n_z, hidden, H, W, B, variant)
 
 
@@ -149,15 +214,16 @@ def make_layers(name, seed=0):
     return layers
 
 
-def make_workload(name, device, nsets, seed=0):
+def make_workload(name, device, nsets, seed=0, B=None):
     from iaf_b200 import IAFOperator
-    variant, n_z, hidden, H, W, B, bound = WORKLOADS[name]
+    variant, n_z, hidden, H, W, Bg, E = WORKLOADS[name]
+    B = Bg if B is None else B
     layers = make_layers(name, seed)
     op = IAFOperator(variant, n_z, hidden, [n_z, n_z], nl="elu", path="auto")
     op.set_weights([tuple(t.to(device) for t in l) for l in layers])
     g = torch.Generator().manual_seed(seed)
     sets = []
-    logdets = torch.zeros((nsets, B), device=device)  # one row per set: the ELBO scalar is one .sum() over it
+    logdets = torch.zeros((nsets, B), device=device)  # one row per set: an ELBO scalar is one .sum() over E rows
     for i in range(nsets):
         z = torch.randn((B, n_z, H, W), generator=g)
         ctx = 0.1 * torch.randn((B, hidden[0], H, W), generator=g)
@@ -167,11 +233,13 @@ def make_workload(name, device, nsets, seed=0):
     return op, layers, sets
 
 
-def cpu_port_runner(name, layers_cpu, sample_B, threads):
+# ----------------------------------------------------------------------------------------------
+# the CPU arm (used by --impl reference directly and, through a subprocess, by the b200 arm)
+# ----------------------------------------------------------------------------------------------
+def cpu_port_runner(name, layers_cpu, sample_B):
     """Returns (fn, elems_per_call): one reference-path IAF step on the host cores."""
     from oracle import iaf_oracle_torch as OT
-    variant, n_z, hidden, H, W, B, _ = WORKLOADS[name]
-    torch.set_num_threads(threads)
+    variant, n_z, hidden, H, W, B, E = WORKLOADS[name]
     g = torch.Generator().manual_seed(0)
     z = torch.randn((sample_B, n_z, H, W), generator=g)
     ctx = 0.1 * torch.randn((sample_B, hidden[0], H, W), generator=g)
@@ -185,30 +253,45 @@ def cpu_port_runner(name, layers_cpu, sample_B, threads):
     return fn, sample_B * n_z * H * W
 
 
-def best_thread_count(fn, max_threads):
-    """The reference's framework would pick its own thread count; more threads than the convs can
-    use makes torch slower, so probe a few settings and keep the fastest."""
-    best, best_t = max_threads, None
-    cands = sorted({c for c in (8, 16, 32, 64, max_threads) if c <= max_threads})
-    for c in cands:
-        torch.set_num_threads(c)
-        fn()
-        t0 = time.perf_counter()
-        fn()
-        dt = time.perf_counter() - t0
-        if best_t is None or dt < best_t:
-            best, best_t = c, dt
-    torch.set_num_threads(best)
-    return best
-
-
-def time_cpu(fn, warmup, steps):
+def _timed_calls(fn, warmup, n):
     for _ in range(warmup):
         fn()
-    t0 = time.perf_counter()
-    for _ in range(steps):
+    ts = []
+    for _ in range(n):
+        t0 = time.perf_counter()
         fn()
-    return (time.perf_counter() - t0) / steps
+        ts.append(time.perf_counter() - t0)
+    return ts
+
+
+def cpu_arm(name, steps, warmup):
+    """The reference's CPU path on this box: returns (seconds per step [median], info dict).  Thread count: the
+    frameworks of the reference pick their own; torch gets slower past what these conv sizes can use, so every candidate
+    (8, 16, the physical cores of one NUMA node, all physical cores) gets 3 warm-up + 5 timed calls and the best median
+    runs the measurement proper (``warmup`` + ``steps`` calls of the full 256-sample batch, median)."""
+    variant, n_z, hidden, H, W, B, E = WORKLOADS[name]
+    allowed, n_phys, n_node = host_topology()
+    layers = make_layers(name)
+    fn, elems = cpu_port_runner(name, layers, B)
+    cands = sorted({c for c in (8, 16, n_node, n_phys) if 1 <= c <= len(allowed)}) or [len(allowed)]
+    cand_ms = {}
+    for c in cands:
+        torch.set_num_threads(c)
+        cand_ms[c] = statistics.median(_timed_calls(fn, 3, 5)) * 1e3
+    best = min(cand_ms, key=cand_ms.get)
+    torch.set_num_threads(best)
+    steps = max(5, min(steps, 50))
+    warmup = max(3, min(warmup, 5))
+    ts = _timed_calls(fn, warmup, steps)
+    t = statistics.median(ts)
+    info = {"value": elems / t, "unit": UNIT, "cores": best, "kind": "port",
+            "sample": "the full %d-sample batch per step, %d warm-up + %d timed steps (median step %.2f ms, min %.2f, "
+                      "max %.2f), torch-CPU fp32 port of the reference path (Theano/TF originals cannot run here)" % (
+                          B, warmup, steps, t * 1e3, min(ts) * 1e3, max(ts) * 1e3),
+            "candidates_ms": {str(k): round(v, 3) for k, v in cand_ms.items()},
+            "host": {"allowed_cpus": len(allowed), "physical_cores": n_phys, "physical_cores_per_numa_node": n_node},
+            "steps": steps, "warmup": warmup}
+    return t, info
 
 
 def run_reference(args, rank, world):
@@ -216,29 +299,229 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     name = args.workload
-    variant, n_z, hidden, H, W, B, bound = WORKLOADS[name]
-    threads = os.cpu_count() or 1
-    layers = make_layers(name)
-    # bounded sample: the full 256-sample batch per step, at most 50 steps
-    sample_B = B
-    fn, elems = cpu_port_runner(name, layers, sample_B, threads)
-    threads = best_thread_count(fn, threads)
-    steps = max(1, min(args.steps, 50))
-    warm = max(1, min(args.warmup, 3))
-    t = time_cpu(fn, warm, steps)
-    value = elems / t
+    variant, n_z, hidden, H, W, B, E = WORKLOADS[name]
+    t, info = cpu_arm(name, args.steps, args.warmup)
+    value = info["value"]
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": warm, "ms_per_step": t * 1e3 * (B / sample_B), "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": info["steps"],
+        "warmup": info["warmup"], "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_string(name), "sample": "%d of %d samples per step, %d steps" % (sample_B, B, steps)},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": "%d of the %d samples per step, %d steps, torch-CPU fp32 port of the "
-                                   "reference path (Theano/TF originals cannot run here)" % (sample_B, B, steps)},
+        "config": {"workload": workload_string(name), "global_batch": B, "timing": "median step, host clock"},
+        "cpu_baseline": info,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_subprocess(name, steps, warmup, full_affinity):
+    """The b200 arm's cpu_baseline leg: the SAME routine, in a fresh process with the original CPU affinity (this process
+    is bound to the GPU's NUMA node and carries a CUDA context, an NVML poller and pinned buffers)."""
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "CUDA_VISIBLE_DEVICES")}
+    env["CUDA_VISIBLE_DEVICES"] = ""
+
+    def unbind():
+        try:
+            os.sched_setaffinity(0, full_affinity)
+        except Exception:
+            pass
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", name,
+                            "--steps", str(steps), "--warmup", str(warmup)], env=env, preexec_fn=unbind,
+                           capture_output=True, text=True, timeout=600)
+        line = json.loads(r.stdout.strip().splitlines()[-1])
+        return line["cpu_baseline"]
+    except Exception as e:  # pragma: no cover
+        return {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": "failed: %r" % (e,)}
+
+
+# ----------------------------------------------------------------------------------------------
+# device-side measurement of one workload
+# ----------------------------------------------------------------------------------------------
+class DeviceBench(object):
+    def __init__(self, name, device, world, rank, dist, use_graph=True):
+        import ctypes as C
+        self.C = C
+        self.name, self.device, self.world, self.rank, self.dist, self.use_graph = name, device, world, rank, dist, use_graph
+        variant, n_z, hidden, H, W, Bg, E = WORKLOADS[name]
+        if Bg % world != 0:
+            raise SystemExit("global batch %d does not divide over %d ranks" % (Bg, world))
+        self.B = Bg // world
+        self.Bg, self.n_z, self.hidden, self.H, self.W, self.E = Bg, n_z, hidden, H, W, E
+        self.alg_bytes_unit = 4 * self.B * H * W * (n_z + hidden[0] + n_z + n_z) + 4 * self.B
+        nsets = max(2, -(-3 * 126 * 2 ** 20 // self.alg_bytes_unit))  # footprint >= 3x the 126 MB L2
+        self.nsets = -(-nsets // E) * E                                # a whole number of ELBO groups
+        self.op, self.layers_cpu, self.sets = make_workload(name, device, self.nsets, B=self.B)
+        self.lib = self.op._lib
+        self.plan = self.op._plan(H, W, device)
+        self.stream = torch.cuda.current_stream(device)
+        self.side = torch.cuda.Stream(device)
+
+    def launch(self, i, st):
+        C = self.C
+        s = self.sets[i % self.nsets]
+        rc = self.lib.iaf_step_fwd(self.plan, C.c_void_p(s["z"].data_ptr()), C.c_void_p(s["ctx"].data_ptr()),
+                                   C.c_void_p(s["z_out"].data_ptr()), C.c_void_p(s["logsd"].data_ptr()),
+                                   C.c_void_p(s["logdet"].data_ptr()), self.B, C.c_void_p(st.cuda_stream))
+        if rc != 0:
+            from iaf_b200 import _lib
+            _lib.check(rc)
+
+    def _capture(self, idxs):
+        """One CUDA graph launching steps ``idxs`` back to back; None when --no-graph or capture is unsupported."""
+        if not self.use_graph:
+            return None
+        try:
+            gstream = torch.cuda.Stream(self.device)
+            gstream.wait_stream(self.stream)
+            with torch.cuda.stream(gstream):
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=gstream):
+                    for i in idxs:
+                        self.launch(i, torch.cuda.current_stream(self.device))
+            self.stream.wait_stream(gstream)
+            return graph
+        except Exception as e:  # capture unsupported -> direct launches (still the CUDA path)
+            self.capture_error = type(e).__name__
+            torch.cuda.synchronize()
+            return None
+
+    def warmup(self, Wm):
+        lc0 = self.op.launch_count()
+        for i in range(Wm):
+            self.launch(i, self.stream)
+        torch.cuda.synchronize()
+        self.launches_per_step = (self.op.launch_count() - lc0) // Wm  # 1 (fused / SIMT) or one per conv stage (layered)
+
+    def _barrier(self):
+        torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
+            torch.cuda.synchronize()
+
+    def _max_over_ranks(self, vals):
+        tt = torch.tensor(vals, device=self.device, dtype=torch.float64)
+        if self.dist is not None:
+            self.dist.all_reduce(tt, op=self.dist.ReduceOp.MAX)
+        return [float(v) for v in tt]
+
+    def time_kernels(self, K):
+        """Kernel-only region: K back-to-back launches (one graph), CUDA events on the launching stream."""
+        g = self._capture(range(K))
+        if g is not None:
+            g.replay()
+        self._barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        if g is not None:
+            g.replay()
+        else:
+            for i in range(K):
+                self.launch(i, self.stream)
+        e1.record()
+        self._barrier()
+        (ms,) = self._max_over_ranks([e0.elapsed_time(e1)])
+        self.launch_mode = "cuda_graph" if g is not None else "direct"
+        return ms * 1e-3 / K
+
+    def time_elbo_groups(self, K):
+        """The job as the model runs it: groups of E steps, each followed by the ELBO scalar (sum of the group's
+        log-dets) and one all-reduce of it across ranks on a side stream.  Returns (seconds per step, launches, scalar)."""
+        E, nsets = self.E, self.nsets
+        groups = [(s, min(E, K - s)) for s in range(0, K, E)]
+        graphs = {}
+        for s, n in groups:
+            key = (s % nsets, n)
+            if key not in graphs:
+                graphs[key] = self._capture(range(s, s + n))
+        scal = torch.zeros((len(groups),), device=self.device)
+        rows = self.op.logdets
+
+        def run():
+            works = []
+            for gi, (s, n) in enumerate(groups):
+                g = graphs[(s % nsets, n)]
+                if g is not None:
+                    g.replay()
+                else:
+                    for i in range(s, s + n):
+                        self.launch(i, self.stream)
+                r0 = s % nsets
+                torch.sum(rows[r0:r0 + n].reshape(-1), dim=0, out=scal[gi])  # the ELBO term of this evaluation on this rank's shard
+                if self.dist is not None:
+                    self.side.wait_stream(self.stream)
+                    with torch.cuda.stream(self.side):
+                        works.append(self.dist.all_reduce(scal[gi], async_op=True))  # tf_train.py:142, one per ELBO
+            if works:
+                with torch.cuda.stream(self.side):
+                    for w in works:
+                        w.wait()
+                self.stream.wait_stream(self.side)
+        run()  # one untimed pass (warms the reduction, the collective and the graphs)
+        self._barrier()
+        l0 = self.op.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run()
+        e1.record()
+        self._barrier()
+        (ms,) = self._max_over_ranks([e0.elapsed_time(e1)])
+        direct = self.op.launch_count() - l0
+        n_launched = direct if direct else K * self.launches_per_step  # graph replays do not pass through the C ABI
+        return ms * 1e-3 / K, int(n_launched), float(scal.sum()), len(groups)
+
+    def roofline(self, t_kernel):
+        hbm_gbs, bf16_tf, peak_src = measured_peaks()
+        op, H, W, dev = self.op, self.H, self.W, self.device
+        alg_bytes = op.algorithmic_bytes(self.B, H, W, dev)
+        alg_flops = op.algorithmic_flops(self.B, H, W, dev)
+        t_hbm, t_tc = alg_bytes / (hbm_gbs * 1e9), alg_flops / (bf16_tf * 1e12)
+        if t_hbm >= t_tc:
+            achieved = alg_bytes / t_kernel / 1e9
+            roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs}
+        else:
+            achieved = alg_flops / t_kernel / 1e12
+            roof = {"bound": "tensor", "achieved": achieved, "peak": bf16_tf, "unit": "TFLOP/s", "frac": achieved / bf16_tf}
+        roof.update({"traffic": None, "kernel": "iaf_step (%s path, %d launch%s per step)" % (
+                         op.path_used(H, W, dev), self.launches_per_step, "" if self.launches_per_step == 1 else "es"),
+                     "kernel_us": t_kernel * 1e6, "algorithmic_bytes": alg_bytes, "algorithmic_flops": alg_flops,
+                     "floor_us": {"hbm": t_hbm * 1e6, "tensor": t_tc * 1e6}, "samples_per_launch": self.B,
+                     "peak_source": peak_src})
+        return roof
+
+    def time_e2e(self, K):
+        """Host buffers through the public API: every step pinned host inputs -> H2D -> step -> D2H of z', arw_logsd,
+        logdet into pinned host outputs (iaf_step_submit_host: three staging slots, so copy-in of step i+1, the kernel of
+        step i and copy-out of step i-1 overlap); the region ends after wait_host().  At least 100 steps and 0.5 s."""
+        op, B, n_z, H, W, hidden, nsets = self.op, self.B, self.n_z, self.H, self.W, self.hidden, self.nsets
+        NH = 4
+        hz = [torch.empty((B, n_z, H, W)).pin_memory().copy_(self.sets[i % nsets]["z"].cpu()) for i in range(NH)]
+        hc = [torch.empty((B, hidden[0], H, W)).pin_memory().copy_(self.sets[i % nsets]["ctx"].cpu()) for i in range(NH)]
+        ho = [torch.empty((B, n_z, H, W)).pin_memory() for _ in range(NH)]
+        hl = [torch.empty((B, n_z, H, W)).pin_memory() for _ in range(NH)]
+        hd = [torch.empty((B,)).pin_memory() for _ in range(NH)]
+
+        def run(n):
+            t0 = time.perf_counter()
+            for i in range(n):
+                op.submit_host(hz[i % NH], hc[i % NH], ho[i % NH], hl[i % NH], hd[i % NH])
+            op.wait_host()
+            return time.perf_counter() - t0
+        run(8)
+        Ke = max(K, 100)
+        self._barrier()
+        t = run(Ke)
+        if t < 0.5:  # too short a window for a host-clock measurement: size it to ~0.6 s and measure again
+            Ke = int(Ke * 0.6 / max(t, 1e-4)) + 1
+            (kmax,) = self._max_over_ranks([float(Ke)])
+            Ke = int(kmax)
+            self._barrier()
+            t = run(Ke)
+        check = float(hd[(Ke - 1) % NH].sum())  # the step's result is read on the host
+        (t,) = self._max_over_ranks([t])
+        h2d = hz[0].numel() * 4 + hc[0].numel() * 4
+        d2h = ho[0].numel() * 4 + hl[0].numel() * 4 + hd[0].numel() * 4
+        return t / Ke, Ke, h2d, d2h, check
 
 
 def main():
@@ -248,8 +531,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2a", choices=sorted(WORKLOADS))  # c2a = the headline
-    ap.add_argument("--no-graph", action="store_true", help="K direct launches instead of one CUDA graph")
+    ap.add_argument("--no-graph", action="store_true", help="direct launches instead of CUDA graphs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the second headline shape")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--batch", type=int, default=0, help="development: override the workload's global batch")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -261,6 +547,8 @@ def main():
         run_reference(args, rank, world)
         return
 
+    full_affinity = set(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else None
+    binding = bind_to_gpu_numa(local_rank)  # before the CUDA context and any pinned allocation
     import __graft_entry__
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
@@ -277,125 +565,57 @@ def main():
         dist.barrier()
 
     name = args.workload
-    variant, n_z, hidden, H, W, B, bound = WORKLOADS[name]
+    if args.batch:
+        WORKLOADS[name] = WORKLOADS[name][:5] + (args.batch,) + WORKLOADS[name][6:]
     K, Wm = args.steps, args.warmup
-    alg_bytes_unit = 4 * B * H * W * (n_z + hidden[0] + n_z + n_z) + 4 * B
-    nsets = max(2, -(-3 * 126 * 2 ** 20 // alg_bytes_unit))  # footprint >= 3x the 126 MB L2
-    op, layers_cpu, sets = make_workload(name, device, nsets)
-    lib = op._lib
-    import ctypes as C
-    plan = op._plan(H, W, device)
-    stream = torch.cuda.current_stream(device)
-
-    def launch(i, st):
-        s = sets[i % nsets]
-        rc = lib.iaf_step_fwd(plan, C.c_void_p(s["z"].data_ptr()), C.c_void_p(s["ctx"].data_ptr()),
-                              C.c_void_p(s["z_out"].data_ptr()), C.c_void_p(s["logsd"].data_ptr()),
-                              C.c_void_p(s["logdet"].data_ptr()), B, C.c_void_p(st.cuda_stream))
-        if rc != 0:
-            from iaf_b200 import _lib
-            _lib.check(rc)
-
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
         sampler.phase = "warmup"
-    lc0 = op.launch_count()
-    for i in range(Wm):
-        launch(i, stream)
-    torch.cuda.synchronize()
-    launches_per_step = (op.launch_count() - lc0) // Wm  # 1 (fused / SIMT kernel) or one per conv stage (layered)
-
-    graph = None
-    launch_mode = "direct"
-    if not args.no_graph:
-        try:
-            gstream = torch.cuda.Stream(device)
-            gstream.wait_stream(stream)
-            with torch.cuda.stream(gstream):
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph, stream=gstream):
-                    for i in range(K):
-                        launch(i, torch.cuda.current_stream(device))
-            stream.wait_stream(gstream)
-            launch_mode = "cuda_graph(%d launches)" % K
-        except Exception as e:  # capture unsupported -> direct launches (still the CUDA path)
-            graph = None
-            launch_mode = "direct (graph capture failed: %s)" % type(e).__name__
-            torch.cuda.synchronize()
-    if graph is not None:
-        graph.replay()  # one untimed replay
-        torch.cuda.synchronize()
-
-    # ---- timed region: device-resident ----
-    launches0 = op.launch_count()
-    ev0, ev1, ev2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-    total = op.logdets.sum()          # warm the reduction (and the collective) outside the timed region
-    if dist is not None:
-        dist.all_reduce(total)
-        dist.barrier()
-    torch.cuda.synchronize()
+    db = DeviceBench(name, device, world, rank, dist, use_graph=not args.no_graph)
+    db.warmup(Wm)
     if sampler:
         sampler.phase = "timed"
-    ev0.record()
-    if graph is not None:
-        graph.replay()
-    else:
-        for i in range(K):
-            launch(i, stream)
-    ev1.record()
-    # the ELBO scalar: sum of log-dets of the sets touched, one all-reduce (tf_train.py:142)
-    total = op.logdets.sum()
-    if dist is not None:
-        dist.all_reduce(total)
-    ev2.record()
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
+    t_kernel = db.time_kernels(K)
+    t_step, n_launched, elbo_sum, n_groups = db.time_elbo_groups(K)
     if sampler:
         sampler.phase = "between"
-    n_launched = K * launches_per_step if graph is not None else op.launch_count() - launches0
-    t_kernels_ms = ev0.elapsed_time(ev1)
-    t_total_ms = ev0.elapsed_time(ev2)
-    tt = torch.tensor([t_total_ms, t_kernels_ms], device=device, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    t_total_ms, t_kernels_ms = float(tt[0]), float(tt[1])
-    elems_step = B * n_z * H * W
-    value = world * elems_step * K / (t_total_ms * 1e-3)
+    elems_step = db.Bg * db.n_z * db.H * db.W
+    value = elems_step / t_step
+    roof = db.roofline(t_kernel)
 
-    # ---- e2e: host buffers through the public API ----
-    # every step: pinned host inputs -> H2D -> step -> D2H of z', arw_logsd, logdet into pinned host outputs.
-    # Steps go through the pipelined public entry (iaf_step_submit_host): three staging slots, so the copy-in
-    # of step i+1, the kernel of step i and the copy-out of step i-1 overlap; the region ends after wait_host().
-    NH = 4
-    hz = [torch.empty((B, n_z, H, W)).pin_memory().copy_(sets[i % nsets]["z"].cpu()) for i in range(NH)]
-    hc = [torch.empty((B, hidden[0], H, W)).pin_memory().copy_(sets[i % nsets]["ctx"].cpu()) for i in range(NH)]
-    ho = [torch.empty((B, n_z, H, W)).pin_memory() for _ in range(NH)]
-    hl = [torch.empty((B, n_z, H, W)).pin_memory() for _ in range(NH)]
-    hd = [torch.empty((B,)).pin_memory() for _ in range(NH)]
-    Ke = K
-    for i in range(4):
-        op.submit_host(hz[i % NH], hc[i % NH], ho[i % NH], hl[i % NH], hd[i % NH])
-    op.wait_host()
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
-    if sampler:
-        sampler.phase = "e2e"
-    t0 = time.perf_counter()
-    for i in range(Ke):
-        op.submit_host(hz[i % NH], hc[i % NH], ho[i % NH], hl[i % NH], hd[i % NH])
-    op.wait_host()
-    t_e2e = time.perf_counter() - t0
-    e2e_check = float(hd[(Ke - 1) % NH].sum())  # the step's result is read on the host
-    te = torch.tensor([t_e2e], device=device, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    t_e2e = float(te[0])
-    e2e_value = world * elems_step * Ke / t_e2e
-    h2d = hz[0].numel() * 4 + hc[0].numel() * 4
-    d2h = ho[0].numel() * 4 + hl[0].numel() * 4 + hd[0].numel() * 4
+    e2e = None
+    if not args.no_e2e:
+        if sampler:
+            sampler.phase = "e2e"
+        t_e2e, Ke, h2d, d2h, check = db.time_e2e(K)
+        e2e = {"value": elems_step / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
+               "ms_per_step": t_e2e * 1e3, "steps": Ke, "logdet_sum_last_step": check, "host_binding": binding,
+               "entry": "IAFOperator.submit_host/wait_host -> iaf_step_submit_host (3-slot H2D/compute/D2H pipeline), "
+                        "every rank its shard of the global batch"}
+        if sampler:
+            sampler.phase = "between"
+
+    # ---- the other headline shape, device-timed in the same run ----
+    also = None
+    if not args.no_also and name == "c2a":
+        other = "c2b"
+        if sampler:
+            sampler.phase = "timed"
+        ob = DeviceBench(other, device, world, rank, dist, use_graph=not args.no_graph)
+        ob.warmup(max(3, Wm // 2))
+        Ko = max(20, min(K, 100))
+        ot_kernel = ob.time_kernels(Ko)
+        ot_step, on_launched, _, o_groups = ob.time_elbo_groups(Ko)
+        o_elems = ob.Bg * ob.n_z * ob.H * ob.W
+        also = {("c2b" if world == 1 else "c5"): {
+            "workload": workload_string(other) + (" (C5: sharded %d/GPU)" % ob.B if world > 1 else ""),
+            "value": o_elems / ot_step, "unit": UNIT, "steps": Ko, "ms_per_step": ot_step * 1e3,
+            "steps_per_elbo": ob.E, "elbo_evaluations": o_groups, "gpu_launches": on_launched,
+            "kernels_per_step": ob.launches_per_step, "roofline": ob.roofline(ot_kernel)}}
+        if sampler:
+            sampler.phase = "between"
+        del ob
     clocks = sampler.finish() if sampler else None
 
     if rank != 0:
@@ -403,58 +623,30 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the step kernel ----
-    hbm_gbs, bf16_tf, peak_src = measured_peaks()
-    t_kernel = t_kernels_ms * 1e-3 / K
-    alg_bytes = op.algorithmic_bytes(B, H, W, device)
-    alg_flops = op.algorithmic_flops(B, H, W, device)
-    traffic = None
-    tj = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tj):
-        with open(tj) as f:
-            traffic = json.load(f).get(name + ":" + op.path_used(H, W, device))
-    if bound == "hbm":
-        achieved = alg_bytes / t_kernel / 1e9
-        roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs}
-    else:
-        achieved = alg_flops / t_kernel / 1e12
-        roof = {"bound": "tensor", "achieved": achieved, "peak": bf16_tf, "unit": "TFLOP/s", "frac": achieved / bf16_tf}
-    roof.update({"traffic": traffic, "kernel": "iaf_step (%s path)" % op.path_used(H, W, device),
-                 "kernel_us": t_kernel * 1e6, "algorithmic_bytes": alg_bytes, "algorithmic_flops": alg_flops,
-                 "peak_source": peak_src})
-
-    # ---- CPU baseline (bounded sample) ----
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        threads = os.cpu_count() or 1
-        sample_B = B
-        fn, elems = cpu_port_runner(name, layers_cpu, sample_B, threads)
-        threads = best_thread_count(fn, threads)
-        t1 = time_cpu(fn, 2, 1)
-        reps = int(max(3, min(200, 15.0 / max(t1, 1e-4))))
-        t = time_cpu(fn, 0, reps)
-        cpu = {"value": elems / t, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "%d of the %d samples per step x %d steps (%.1f s), torch-CPU fp32 port of the "
-                         "reference path" % (sample_B, B, reps, t * reps)}
+        cpu = cpu_baseline_subprocess(name, 20, 3, full_affinity)
 
+    path = db.op.path_used(db.H, db.W, device)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
-        "ms_per_step": t_total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32 (tc path: bf16x3 split operands, f32 accumulate)" if op.path_used(H, W, device) == "tc" else "f32",
+        "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32 (tc path: bf16x3 split operands, f32 accumulate)" if path == "tc" else "f32",
         "data": "synthetic",
-        "config": {"workload": workload_string(name), "global_batch": B * world, "parallelism": "dp%d" % world,
-                   "path": op.path_used(H, W, device), "launch": launch_mode, "kernels_per_step": launches_per_step,
-                   "l2": "rotating %d input/output sets (%.0f MB > 126 MB L2)" % (nsets, nsets * alg_bytes_unit / 2 ** 20),
-                   "collective": "one all-reduce of the scalar sum(logdet) per timed region" if world > 1 else "none",
-                   "samples_per_s": value / (n_z * H * W)},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": t_e2e / Ke * 1e3, "steps": Ke, "logdet_sum_last_step": e2e_check,
-                "entry": "IAFOperator.submit_host/wait_host -> iaf_step_submit_host (3-slot H2D/compute/D2H pipeline)"},
+        "config": {"workload": workload_string(name), "global_batch": db.Bg, "samples_per_gpu": db.B,
+                   "parallelism": "dp%d" % world, "path": path, "launch": db.launch_mode,
+                   "kernels_per_step": db.launches_per_step, "steps_per_elbo": db.E, "elbo_evaluations": n_groups,
+                   "l2": "rotating %d input/output sets (%.0f MB > 126 MB L2)" % (db.nsets, db.nsets * db.alg_bytes_unit / 2 ** 20),
+                   "collective": ("one NCCL all-reduce of the ELBO scalar per evaluation (%d steps), on a side stream"
+                                  % db.E) if world > 1 else "none",
+                   "samples_per_s": value / (db.n_z * db.H * db.W)},
+        "e2e": e2e,
         "gpu_launches": int(n_launched),
         "clocks": clocks,
         "roofline": roof,
         "cpu_baseline": cpu,
-        "elbo_scalar": float(total),
+        "also": also,
+        "elbo_scalar": elbo_sum,
     }
     print(json.dumps(line), flush=True)
     if dist is not None:

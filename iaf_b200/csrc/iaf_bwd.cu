@@ -778,9 +778,8 @@ int iaf_bwd_plan_create(IafBwdPlan** out, const iaf_desc_t* d, const int* cin, c
     pl->wg_smem = 2 * sizeof(float) * WG_S * ((size_t)(rb + 1) * PW + (size_t)rb * d->W);
   }
   pl->wg_RB = rb;
-  if (cudaFuncSetAttribute(iaf_bwd_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->wg_smem) != cudaSuccess ||
-      cudaFuncSetAttribute(iaf_lconv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess ||
-      cudaFuncSetAttribute(iaf_lconv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess) {
+  if (iaf_smem_optin(iaf_bwd_wgrad_kernel) != cudaSuccess || iaf_smem_optin(iaf_lconv_kernel<false>) != cudaSuccess ||
+      iaf_smem_optin(iaf_lconv_kernel<true>) != cudaSuccess) {
     iaf_bwd_plan_destroy(pl);
     return IAF_ERR_CUDA;
   }

@@ -175,7 +175,13 @@ int iaf_plan_create(iaf_plan_t** out, const iaf_desc_t* desc) {
   if (!pl) return IAF_ERR_BAD_ARG;
   memset(pl, 0, sizeof(*pl));
   pl->d = d;
-  CK(cudaGetDevice(&pl->device));
+  // a CUDA failure from here on releases the half-built plan (struct and device buffers) before returning
+#define CKP(call)                                                    \
+  do {                                                              \
+    cudaError_t e_ = (call);                                        \
+    if (e_ != cudaSuccess) { iaf_plan_destroy(pl); return cuda_fail(e_, #call); } \
+  } while (0)
+  CKP(cudaGetDevice(&pl->device));
   pl->n_stages = d.n_hidden + 1;
   int prev = d.n_z;
   for (int j = 0; j < pl->n_stages; ++j) {
@@ -194,10 +200,11 @@ int iaf_plan_create(iaf_plan_t** out, const iaf_desc_t* desc) {
     }
     prev = pl->cout[j];
     pl->w_elems[j] = (size_t)IAF_NTAPS * pl->cin[j] * pl->cout_pad[j];
-    CK(cudaMalloc(&pl->w[j], sizeof(float) * pl->w_elems[j]));
-    CK(cudaMalloc(&pl->bias[j], sizeof(float) * pl->cout_pad[j]));
-    CK(cudaMalloc(&pl->padw[j], sizeof(float) * 4 * pl->cout_pad[j]));
+    CKP(cudaMalloc(&pl->w[j], sizeof(float) * pl->w_elems[j]));
+    CKP(cudaMalloc(&pl->bias[j], sizeof(float) * pl->cout_pad[j]));
+    CKP(cudaMalloc(&pl->padw[j], sizeof(float) * 4 * pl->cout_pad[j]));
   }
+#undef CKP
   // SIMT geometry: the largest band that leaves room for two CTAs per SM, else the largest that fits at all
   const size_t kTwo = 100 * 1024, kMax = 225 * 1024;
   int chosen = 0;
@@ -233,7 +240,7 @@ int iaf_plan_create(iaf_plan_t** out, const iaf_desc_t* desc) {
     }
   }
   if (simt_ok) {
-    cudaError_t e = iaf_simt_set_smem(pl->smem);
+    cudaError_t e = iaf_simt_set_smem();
     if (e != cudaSuccess) { iaf_plan_destroy(pl); return cuda_fail(e, "cudaFuncSetAttribute(simt smem)"); }
   }
   *out = pl;

@@ -19,6 +19,26 @@ __device__ __forceinline__ void iaf_cp_async4(float* dst, const float* src, bool
 __device__ __forceinline__ void iaf_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void iaf_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 #endif
+// Raise a kernel's dynamic shared-memory limit to everything the device allows (opt-in maximum minus the kernel's static
+// shared memory).  The attribute is per kernel, not per plan: setting it to one plan's size would LOWER it for plans
+// created earlier with a larger footprint, so it is only ever set to the device maximum (idempotent).
+template <class K>
+static inline cudaError_t iaf_smem_optin(K kernel) {
+#ifdef IAF_EMU
+  (void)kernel;
+  return cudaSuccess;
+#else
+  int dev = 0, optin = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (e != cudaSuccess) return e;
+  cudaFuncAttributes fa;
+  e = cudaFuncGetAttributes(&fa, kernel);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+#endif
+}
 #include <stdint.h>
 #include "../../include/iaf_b200.h"
 
@@ -88,4 +108,4 @@ struct IafPackParams {
 
 cudaError_t iaf_launch_pack(const IafPackParams& p, int max_cout, cudaStream_t stream);
 cudaError_t iaf_launch_simt(const IafSimtParams& p, size_t smem_bytes, cudaStream_t stream);
-cudaError_t iaf_simt_set_smem(size_t smem_bytes);
+cudaError_t iaf_simt_set_smem();

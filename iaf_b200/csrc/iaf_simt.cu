@@ -281,8 +281,8 @@ __global__ void __launch_bounds__(IAF_SIMT_THREADS, 2) iaf_simt_kernel(const __g
   }
 }
 
-cudaError_t iaf_simt_set_smem(size_t smem_bytes) {
-  return cudaFuncSetAttribute(iaf_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+cudaError_t iaf_simt_set_smem() {
+  return iaf_smem_optin(iaf_simt_kernel);
 }
 
 cudaError_t iaf_launch_simt(const IafSimtParams& p, size_t smem_bytes, cudaStream_t stream) {

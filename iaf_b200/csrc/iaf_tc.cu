@@ -48,9 +48,9 @@
 #define TC_RED_WARP (TC_WORKERS + 1)
 #define TC_TILE 128
 #ifdef IAF_TC_TIMELINE
-#define TC_SMEM_LIMIT (227 * 1024 - 2048 - 6144)  // room for the static event buffers
+#define TC_SMEM_LIMIT (227 * 1024 - 512 - 2560)  // room for the static event buffers
 #else
-#define TC_SMEM_LIMIT (227 * 1024 - 2048)
+#define TC_SMEM_LIMIT (227 * 1024 - 512)  // opt-in maximum minus the kernels' static shared memory (barriers: < 512 B)
 #endif
 #ifndef TC_NGROUPS
 #define TC_NGROUPS 1   // 1: all 16 worker warps run every phase together; 2: two ping-pong groups by tile parity
@@ -110,6 +110,12 @@ struct IafTcParams {
   int prefetch;  // IAF_TC_PREFETCH: 1 bulk L2 prefetch of this CTA's context range at kernel start, 2: context and z,
                  // 4: per-thread prefetch.global.L2 of the next tile's z window / context one period ahead
   unsigned mg_sps, mg_wp, mg_win;  // magic multipliers for fast_div
+  // iaf_fz_kernel (one hidden layer, independent overlapped tiles) only:
+  int TO;        // output slots per tile (128 - MIR)
+  int h_bytes;   // bytes of one hidden-activation operand buffer (hi + lo plane sets of 128 slots)
+  int z_bytes;   // bytes of one z operand window (hi + lo plane sets of WIN slots, rounded up to 128)
+  int dbg;       // IAF_FZ_DBG (development, timing only, results WRONG when set): 1 loaders issue no global loads,
+                 // 2 loaders also skip their stores, 4 E0 does nothing but the hand-off, 8 E1 likewise, 16 no MMAs, 32 no weight load
 };
 
 // ------------------------------------------------------------------------------------------
@@ -275,11 +281,11 @@ __device__ __forceinline__ void split_store8(const float* v, uint8_t* hi_ptr, ui
 // Optional in-kernel timeline (compile with -DIAF_TC_TIMELINE; development aid only): CTA 0 records
 // (tag, tile, clock) triples for the control lane and lane 0 of the first warp of each worker group.
 #ifdef IAF_TC_TIMELINE
-#define TL_MAX 64
-__device__ long long g_tl[3][TL_MAX][3];
-__device__ int g_tl_n[3];
+#define TL_MAX 26
+__device__ long long g_tl[4][TL_MAX][3];
+__device__ int g_tl_n[4];
 // events are staged in shared memory (a global counter would cost an L2 round trip per event)
-#define TL_DECL __shared__ long long s_tl[3][TL_MAX][3]; __shared__ int s_tl_n[3]; if (threadIdx.x < 3) s_tl_n[threadIdx.x] = 0;
+#define TL_DECL __shared__ long long s_tl[4][TL_MAX][3]; __shared__ int s_tl_n[4]; if (threadIdx.x < 4) s_tl_n[threadIdx.x] = 0;
 #define TL(role, tag, kk)                                                          \
   do {                                                                             \
     if (blockIdx.x == 0) {                                                         \
@@ -288,7 +294,7 @@ __device__ int g_tl_n[3];
     }                                                                              \
   } while (0)
 #define TL_FLUSH                                                                   \
-  if (blockIdx.x == 0 && threadIdx.x < 3) {                                        \
+  if (blockIdx.x == 0 && threadIdx.x < 4) {                                        \
     const int r_ = threadIdx.x;                                                    \
     for (int i_ = 0; i_ < s_tl_n[r_]; ++i_)                                        \
       for (int c_ = 0; c_ < 3; ++c_) g_tl[r_][i_][c_] = s_tl[r_][i_][c_];          \
@@ -1005,6 +1011,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
 }
 
 #include "iaf_tc_gemm.cuh"
+#include "iaf_fz.cuh"
 
 // ------------------------------------------------------------------------------------------
 // weight preparation for this path: same math as iaf_pack.cu, bf16 hi/lo split, written as
@@ -1108,6 +1115,9 @@ struct IafTcPlan {
   int sm_bias[IAF_MAX_STAGES], tmem_col[IAF_MAX_STAGES], dbl[IAF_MAX_STAGES], merged[IAF_MAX_STAGES], acc_cols[IAF_MAX_STAGES];
   int MIR, WIN, RING, MAXS, sm_part, tmem_cols;
   bool layer_ok;             // the per-(sample,channel) scratch of the fused-layer mode fits
+  // second-generation fused kernel (iaf_fz_kernel: exactly one hidden layer)
+  bool fz;
+  int TO, h_bytes, z_bytes;
   // layer-at-a-time mode (hidden widths that do not fit the fused kernel's on-chip rings)
   bool layered;
   int ly_stage[IAF_MAX_STAGES];
@@ -1160,7 +1170,88 @@ static LyKernel ly_kernel_for(bool padw, int mode, bool elu, int hw) {
   return hw == 256 ? ly_kernel_pick<256>(padw, mode, elu) : ly_kernel_pick<0>(padw, mode, elu);
 }
 
+template <int THW>
+static TcKernel fz_kernel_pick(bool padw, int mode, bool elu) {
+  if (mode == IAF_MODE_MULTICONV) {
+    if (padw) return elu ? iaf_fz_kernel<true, IAF_MODE_MULTICONV, IAF_NL_ELU, THW> : iaf_fz_kernel<true, IAF_MODE_MULTICONV, -1, THW>;
+    return elu ? iaf_fz_kernel<false, IAF_MODE_MULTICONV, IAF_NL_ELU, THW> : iaf_fz_kernel<false, IAF_MODE_MULTICONV, -1, THW>;
+  }
+  if (mode == IAF_MODE_STEP) {
+    if (padw) return elu ? iaf_fz_kernel<true, IAF_MODE_STEP, IAF_NL_ELU, THW> : iaf_fz_kernel<true, IAF_MODE_STEP, -1, THW>;
+    return elu ? iaf_fz_kernel<false, IAF_MODE_STEP, IAF_NL_ELU, THW> : iaf_fz_kernel<false, IAF_MODE_STEP, -1, THW>;
+  }
+  if (padw) return elu ? iaf_fz_kernel<true, IAF_MODE_LAYER, IAF_NL_ELU, THW> : iaf_fz_kernel<true, IAF_MODE_LAYER, -1, THW>;
+  return elu ? iaf_fz_kernel<false, IAF_MODE_LAYER, IAF_NL_ELU, THW> : iaf_fz_kernel<false, IAF_MODE_LAYER, -1, THW>;
+}
+static TcKernel fz_kernel_for(bool padw, int mode, bool elu, int hw) {
+  return hw == 256 ? fz_kernel_pick<256>(padw, mode, elu) : fz_kernel_pick<0>(padw, mode, elu);
+}
+
 static int tc_round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// iaf_fz_kernel: one hidden layer; weights resident, one z window, two hidden-activation buffers, both accumulators
+// double-buffered in TMEM
+static bool fz_layout(const iaf_desc_t* d, IafTcPlan* pl) {
+  if (d->n_hidden != 1 || d->n_heads != 2 || d->head[0] != d->n_z || d->head[1] != d->n_z) return false;
+  if (d->n_z % 16 != 0 || 2 * d->n_z > 256) return false;
+  if (d->hidden[0] % 16 != 0 || d->hidden[0] > 256) return false;
+  const int Wp = d->W + 1;
+  const int SPS = (d->H + 1) * Wp;
+  const int MIR = Wp + 1;  // largest tap shift
+  const int TO = TC_TILE - MIR;
+  if (TO < TC_TILE / 2) return false;
+  IafTcPlan tmp;
+  IafTcPlan* q = pl ? pl : &tmp;
+  q->n_stages = 2;
+  q->MIR = MIR; q->WIN = TC_TILE + MIR; q->RING = 0; q->TO = TO;
+  q->MAXS = (TO - 1) / SPS + 2;
+  int off = 0, prev = d->n_z;
+  for (int j = 0; j < 2; ++j) {
+    q->cin[j] = prev;
+    q->N[j] = (j == 0) ? d->hidden[0] : 2 * d->n_z;
+    q->K[j] = IAF_NTAPS * prev;
+    const int wb = q->K[j] * q->N[j] * 2;
+    q->sm_whi[j] = off; off += wb;
+    q->sm_wlo[j] = off; off += wb;
+    prev = q->N[j];
+  }
+  q->in_slots[0] = q->WIN;
+  q->sm_in[0] = off;
+  q->z_bytes = tc_round_up(2 * (q->cin[0] / 8) * q->WIN * 16, 128);
+  off += 2 * q->z_bytes;  // two z windows: the loaders run a full tile ahead of the MMAs
+  if ((q->cin[0] / 8) * q->WIN > FZ_ZB * FZ_LTHREADS || q->N[0] > 16 * FZ_CXG * FZ_LGS) return false;
+  q->in_slots[1] = TC_TILE;
+  q->sm_in[1] = off;
+  q->h_bytes = 2 * (q->cin[1] / 8) * TC_TILE * 16;
+  off += 2 * q->h_bytes;
+  off += tc_round_up(MIR * 16, 128);  // a shifted 128-row window of the last plane reads MIR rows past the buffer
+  for (int j = 0; j < 2; ++j) {
+    q->sm_bias[j] = off;
+    off += 5 * q->N[j] * 4;
+  }
+  off = tc_round_up(off, 16);
+  q->sm_part = off;
+  const int part_step = 2 * FZ_EPI * q->MAXS * 4;
+  const int part_layer = 2 * 4 * q->MAXS * d->n_z * 4;
+  if (q->MAXS > 32) return false;  // the reducer warp keeps one per-sample value per lane ...
+  q->layer_ok = (off + std::max(part_step, part_layer)) <= TC_SMEM_LIMIT && q->MAXS * d->n_z <= 256;  // ... 8 in layer mode
+  off += q->layer_ok ? std::max(part_step, part_layer) : part_step;
+  // TMEM: both accumulators double-buffered; what is left goes to the merged hi*[hi|lo] form, the heads first
+  int cols = 2 * (q->N[0] + q->N[1]);
+  if (cols > 512) return false;
+  const char* mg = getenv("IAF_TC_MERGED");
+  for (int j = 0; j < 2; ++j) { q->dbl[j] = 1; q->merged[j] = 0; q->acc_cols[j] = q->N[j]; }
+  for (int j = 1; j >= 0 && !(mg && mg[0] == '0'); --j) {
+    if (2 * q->N[j] <= 256 && cols + 2 * q->N[j] <= 512) { q->merged[j] = 1; q->acc_cols[j] = 2 * q->N[j]; cols += 2 * q->N[j]; }
+  }
+  int col = 0;
+  for (int j = 0; j < 2; ++j) { q->tmem_col[j] = col; col += 2 * q->acc_cols[j]; }
+  int tc = 32;
+  while (tc < col) tc *= 2;
+  q->tmem_cols = tc;
+  q->smem = (size_t)off;
+  return off <= TC_SMEM_LIMIT;
+}
 
 static bool tc_layout(const iaf_desc_t* d, IafTcPlan* pl) {
   if (d->n_hidden < 1 || d->n_heads != 2 || d->head[0] != d->n_z || d->head[1] != d->n_z) return false;
@@ -1273,7 +1364,7 @@ static bool ly_layout(const iaf_desc_t* d, IafTcPlan* pl) {
   return true;
 }
 
-bool iaf_tc_supported(const iaf_desc_t* d) { return tc_layout(d, nullptr) || ly_layout(d, nullptr); }
+bool iaf_tc_supported(const iaf_desc_t* d) { return fz_layout(d, nullptr) || tc_layout(d, nullptr) || ly_layout(d, nullptr); }
 
 int iaf_tc_plan_create(IafTcPlan** out, const iaf_desc_t* d) {
   IafTcPlan* pl = new (std::nothrow) IafTcPlan();
@@ -1281,8 +1372,12 @@ int iaf_tc_plan_create(IafTcPlan** out, const iaf_desc_t* d) {
   memset(pl, 0, sizeof(*pl));
   pl->d = *d;
   pl->layered = false;
+  pl->fz = false;
   const char* force = getenv("IAF_TC_FORCE_LAYERED");  // development switch: compare the two tensor-core schedules
-  if ((force && force[0] == '1') || !tc_layout(d, pl)) {
+  const char* nofz = getenv("IAF_TC_FZ");              // development switch: IAF_TC_FZ=0 keeps the first-generation kernel
+  if (!(force && force[0] == '1') && !(nofz && nofz[0] == '0') && fz_layout(d, pl)) {
+    pl->fz = true;
+  } else if ((force && force[0] == '1') || !tc_layout(d, pl)) {
     if (!ly_layout(d, pl)) { delete pl; return IAF_ERR_UNSUPPORTED; }
     pl->layered = true;
   }
@@ -1293,24 +1388,23 @@ int iaf_tc_plan_create(IafTcPlan** out, const iaf_desc_t* d) {
   pl->num_sms = prop.multiProcessorCount;
   for (int j = 0; j < pl->n_stages; ++j) {
     const size_t wb = (size_t)pl->K[j] * pl->N[j] * 2;
+    // bias [N] and pad-channel weights [4][N] are ONE table [5][N] (iaf_fz_kernel fetches it with a single bulk copy)
     if (cudaMalloc(&pl->whi[j], 2 * wb) != cudaSuccess || cudaMalloc(&pl->wlo[j], wb) != cudaSuccess ||
-        cudaMalloc(&pl->bias[j], sizeof(float) * pl->N[j]) != cudaSuccess ||
-        cudaMalloc(&pl->padw[j], sizeof(float) * 4 * pl->N[j]) != cudaSuccess) {
+        cudaMalloc(&pl->bias[j], sizeof(float) * 5 * pl->N[j]) != cudaSuccess) {
       iaf_tc_plan_destroy(pl);
       return IAF_ERR_CUDA;
     }
+    pl->padw[j] = pl->bias[j] + pl->N[j];
   }
-  size_t ly_max = 0;
-  for (int j = 0; j < pl->n_stages; ++j) ly_max = std::max(ly_max, pl->ly_smem[j]);
   for (int a = 0; a < 12; ++a) {
     cudaError_t e;
     const int md = (a >> 2) == 0 ? IAF_MODE_MULTICONV : ((a >> 2) == 1 ? IAF_MODE_STEP : IAF_MODE_LAYER);
-    if (pl->layered)
-      e = cudaFuncSetAttribute(ly_kernel_for(a & 1, md, a & 2, d->H * d->W), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)ly_max);
+    if (pl->fz)
+      e = iaf_smem_optin(fz_kernel_for(a & 1, md, a & 2, d->H * d->W));
+    else if (pl->layered)
+      e = iaf_smem_optin(ly_kernel_for(a & 1, md, a & 2, d->H * d->W));
     else
-      e = cudaFuncSetAttribute(tc_kernel_for(a & 1, md, a & 2, d->H * d->W), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)pl->smem);
+      e = iaf_smem_optin(tc_kernel_for(a & 1, md, a & 2, d->H * d->W));
     if (e != cudaSuccess) {
       iaf_tc_plan_destroy(pl);
       return IAF_ERR_CUDA;
@@ -1325,8 +1419,7 @@ void iaf_tc_plan_destroy(IafTcPlan* pl) {
   for (int j = 0; j < IAF_MAX_STAGES; ++j) {
     if (pl->whi[j]) cudaFree(pl->whi[j]);
     if (pl->wlo[j]) cudaFree(pl->wlo[j]);
-    if (pl->bias[j]) cudaFree(pl->bias[j]);
-    if (pl->padw[j]) cudaFree(pl->padw[j]);
+    if (pl->bias[j]) cudaFree(pl->bias[j]);  // padw[j] points into the same allocation
   }
   if (pl->counter) cudaFree(pl->counter);
   if (pl->tilepart) cudaFree(pl->tilepart);
@@ -1372,19 +1465,39 @@ int iaf_tc_pack(IafTcPlan* pl, const float* const* w, const float* const* scale,
 #ifdef IAF_TC_TIMELINE
 extern "C" void iaf_tc_timeline_dump(void) {
   cudaDeviceSynchronize();
-  static long long h[3][TL_MAX][3];
-  int n[3];
+  static long long h[4][TL_MAX][3];
+  int n[4];
   cudaMemcpyFromSymbol(h, g_tl, sizeof(h));
   cudaMemcpyFromSymbol(n, g_tl_n, sizeof(n));
   long long t0 = -1;
-  for (int r = 0; r < 3; ++r)
+  for (int r = 0; r < 4; ++r)
     for (int i = 0; i < n[r] && i < TL_MAX; ++i)
       if (t0 < 0 || h[r][i][2] < t0) t0 = h[r][i][2];
-  for (int r = 0; r < 3; ++r)
+  for (int r = 0; r < 4; ++r)
     for (int i = 0; i < n[r] && i < TL_MAX; ++i)
       printf("TL role=%d tag=%lld k=%lld t=%lld\n", r, h[r][i][0], h[r][i][1], h[r][i][2] - t0);
-  int z[3] = {0, 0, 0};
+  int z[4] = {0, 0, 0, 0};
   cudaMemcpyToSymbol(g_tl_n, z, sizeof(z));
+}
+#endif
+
+#ifdef IAF_FZ_PROBE
+extern "C" void iaf_fz_probe_dump(void) {
+  cudaDeviceSynchronize();
+  long long h[4][8];
+  cudaMemcpyFromSymbol(h, g_fz_probe, sizeof(h));
+  static const char* names[3][8] = {
+      {"wait ZFULL", "wait A0_INIT", "issue M0", "wait H_FULL", "wait A1_EMPTY", "issue M1", "wait weights", "loop glue"},
+      {"issue loads", "wait tables", "wait A0_EMPTY", "ctx -> TMEM", "wait ZEMPTY", "z -> smem", "-", "-"},
+      {"wait A0_FULL", "wait H_EMPTY", "E0 body", "E1 loads + wait A1_FULL", "E1 body", "wait PART_EMPTY", "wait tables", "loop glue"}};
+  static const char* roles[3] = {"MMA warp", "loader warp 0", "epilogue warp 0"};
+  for (int r = 0; r < 3; ++r) {
+    long long tot = 0;
+    for (int i = 0; i < 8; ++i) tot += h[r][i];
+    printf("PROBE %-16s total %7lld :", roles[r], tot);
+    for (int i = 0; i < 8; ++i) printf("  %s %lld", names[r][i], h[r][i]);
+    printf("\n");
+  }
 }
 #endif
 
@@ -1399,7 +1512,8 @@ int iaf_tc_run(IafTcPlan* pl, const IafTcArgs* a, cudaStream_t stream, int* n_la
   const int SPS = (d.H + 1) * (d.W + 1);
   if ((long long)B * SPS + TC_TILE >= (1LL << 31)) return IAF_ERR_UNSUPPORTED;
   const int S = B * SPS;
-  const int NT = (S + TC_TILE - 1) / TC_TILE;
+  const int tile_step = pl->fz ? pl->TO : TC_TILE;  // output slots per tile
+  const int NT = (S + tile_step - 1) / tile_step;
   if (B > pl->scratch_B) {
     if (pl->counter) cudaFree(pl->counter);
     if (pl->tilepart) cudaFree(pl->tilepart);
@@ -1453,6 +1567,8 @@ int iaf_tc_run(IafTcPlan* pl, const IafTcArgs* a, cudaStream_t stream, int* n_la
   p.mg_sps = (unsigned)((1ULL << 32) / (unsigned)SPS) + 1u;
   p.mg_wp = (unsigned)((1ULL << 32) / (unsigned)p.Wp) + 1u;
   p.mg_win = (unsigned)((1ULL << 32) / (unsigned)p.WIN) + 1u;
+  p.TO = pl->TO; p.h_bytes = pl->h_bytes; p.z_bytes = pl->z_bytes;
+  { const char* dbg = getenv("IAF_FZ_DBG"); p.dbg = dbg ? atoi(dbg) : 0; }
   const int grid = std::min(pl->num_sms, NT);
   if (pl->layered) {
     LyKernel lk = ly_kernel_for(d.variant == IAF_VARIANT_THEANO, a->mode, d.nl == IAF_NL_ELU, d.H * d.W);
@@ -1507,12 +1623,14 @@ int iaf_tc_run(IafTcPlan* pl, const IafTcArgs* a, cudaStream_t stream, int* n_la
     if (n_launches) *n_launches = pl->n_stages;
     return cudaGetLastError() == cudaSuccess ? IAF_OK : IAF_ERR_CUDA;
   }
-  TcKernel k = tc_kernel_for(d.variant == IAF_VARIANT_THEANO, a->mode, d.nl == IAF_NL_ELU, d.H * d.W);
+  TcKernel k = pl->fz ? fz_kernel_for(d.variant == IAF_VARIANT_THEANO, a->mode, d.nl == IAF_NL_ELU, d.H * d.W)
+                      : tc_kernel_for(d.variant == IAF_VARIANT_THEANO, a->mode, d.nl == IAF_NL_ELU, d.H * d.W);
   {
     const char* e = getenv("IAF_PDL");
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = pl->smem; cfg.stream = stream;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(pl->fz ? FZ_THREADS : TC_THREADS); cfg.dynamicSmemBytes = pl->smem;
+    cfg.stream = stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = (e && e[0] == '0') ? 0 : 1;

@@ -166,10 +166,12 @@ class CudaIAF(object):
         if op is None:
             zs, hs = self.hps["z_size"], self.hps["h_size"]
             op = self.IAFOperator("tf", zs, [hs, hs], [zs, zs], nl="elu", path=self.path)   # tf_train.py:69
-            pre = scope + "/ar_multiconv2d/"
-            op.set_weights([tuple(self.params[pre + n + "/" + k] for k in "Vgb")
-                            for n in ("layer_0", "layer_1", "layer_out_0", "layer_out_1")])
             self.ops[scope] = op
+        # re-bound on every call: replacing an entry of the params dict (checkpoint load, optimiser that rebinds) is
+        # picked up; unchanged tensors keep the packed copy (key = storage + version, see IAFOperator._weights_key)
+        pre = scope + "/ar_multiconv2d/"
+        op.set_weights([tuple(self.params[pre + n + "/" + k] for k in "Vgb")
+                        for n in ("layer_0", "layer_1", "layer_out_0", "layer_out_1")])
         z, _, kl_bc, kl_cost = op.layer(eps, post_mean, post_logsd, prior_mean, prior_logsd, context, want_kl=False)
         return z, kl_bc, kl_cost
 

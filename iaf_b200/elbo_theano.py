@@ -219,6 +219,12 @@ class CudaIAF(object):
             self.ops[name] = op
         return op
 
+    def invalidate(self):
+        """The inference wrapper converts ``w`` (numpy or torch) to device tensors ONCE per layer; after changing or
+        replacing entries of ``w`` call this so the next evaluation re-imports and re-packs them."""
+        self.ops.clear()
+        return self
+
     def __call__(self, name, eps, post_mean, post_logsd, prior_mean, prior_logsd, context):
         z, _, kl_bc, kl_cost = self._op(name, eps.device).layer(eps, post_mean, post_logsd, prior_mean, prior_logsd,
                                                                 context, want_kl=False)

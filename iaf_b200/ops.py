@@ -73,6 +73,7 @@ class IAFOperator(object):
             raise NotImplementedError("n_out must have 1 or 2 entries")
         self.variant, self.n_z, self.hidden, self.heads, self.nl, self.path = variant, int(n_z), hidden, heads, nl, path
         self._layers = None
+        self._epoch = 0       # bumped by set_weights()/invalidate(): part of the packed-weights cache key
         self._plans = {}      # (H, W, device index) -> [handle, packed_key]
         self._lib = _lib.lib()
 
@@ -89,11 +90,28 @@ class IAFOperator(object):
             wshape = (3, 3, cin, cout) if self.variant == "tf" else (cout, cin + 1, 3, 3)
             out.append((_check_input(w, "w[%d]" % i, wshape), _check_input(s, "scale[%d]" % i, (cout,)),
                         _check_input(b, "bias[%d]" % i, (cout,))))
+        same = self._layers is not None and len(self._layers) == len(out) and all(
+            a is b for la, lb in zip(self._layers, out) for a, b in zip(la, lb))
         self._layers = out
+        if not same:
+            self._epoch += 1  # different tensor objects: never reuse a packed copy across a re-binding
         return self
 
     def _weights_key(self, layers=None):
-        return tuple((t.data_ptr(), t._version) for l in (self._layers if layers is None else layers) for t in l)
+        """Identity of the packed weights: (storage, version counter) of every parameter tensor plus the operator's own
+        epoch.  In-place updates through ``.data`` (``p.data.copy_``, the usual spelling in older training loops and in
+        ports of the reference's ``postup``) do NOT bump ``_version``; callers that update parameters that way call
+        ``invalidate()`` (or ``set_weights`` again, which does).  While any parameter requires grad the packed copy is
+        not trusted at all and every call re-packs (two small launches)."""
+        ls = self._layers if layers is None else layers
+        if torch.is_grad_enabled() and any(t.requires_grad for l in ls for t in l):
+            self._epoch += 1
+        return (self._epoch,) + tuple((t.data_ptr(), t._version) for l in ls for t in l)
+
+    def invalidate(self):
+        """Forget the packed weights: the next call re-runs iaf_pack_weights from the raw parameter tensors."""
+        self._epoch += 1
+        return self
 
     def _needs_grad(self, *tensors):
         if not torch.is_grad_enabled():
