@@ -12,6 +12,7 @@ VARIANTS = {"tf": 0, "theano": 1}
 NLS = {None: 0, "None": 0, "none": 0, "elu": 1, "softplus": 2, "relu": 3, "tanh": 4, "leakyrelu": 5}
 PATHS = {"auto": 0, "simt": 1, "tc": 2}
 PATH_NAMES = {1: "simt", 2: "tc"}
+ENTRIES = {"multiconv": 0, "step": 1, "layer": 2}
 
 OK, ERR_BAD_ARG, ERR_BAD_SHAPE, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOT_PACKED, ERR_NO_DEVICE = 0, -1, -2, -3, -4, -5, -6
 
@@ -49,6 +50,7 @@ SYMBOLS = {
     "iaf_last_cuda_error": (C.c_char_p, []),
     "iaf_version": (C.c_int, []),
     "iaf_plan_path": (C.c_int, [_P]),
+    "iaf_plan_path_for_entry": (C.c_int, [_P, C.c_int]),
     "iaf_plan_launch_count": (C.c_uint64, [_P]),
     "iaf_plan_algorithmic_bytes": (C.c_size_t, [_P, C.c_int]),
     "iaf_plan_algorithmic_flops": (C.c_double, [_P, C.c_int]),

@@ -81,6 +81,11 @@ struct iaf_plan {
   // backward (created on the first iaf_*_bwd call)
   IafBwdPlan* bwd;
   uint64_t launches;
+  // a plan's scratch (partial sums, counters, packed weights, operand images) serves ONE stream at a time: when a call
+  // arrives on a different stream than the previous one, the new stream first waits for the old one's work
+  cudaStream_t last_stream;
+  bool last_stream_valid;
+  cudaEvent_t ev_handoff;
 };
 #define IAF_NSLOT 3
 
@@ -108,6 +113,28 @@ static bool simt_geometry(iaf_plan* pl, int band_rows, size_t* smem_out) {
   pl->bufz = bufz; pl->bufa = bufa; pl->bufb = bufb; pl->tilepart = tilepart;
   pl->smem = smem;
   return true;
+}
+
+// Order this call after the plan's previous call when the stream changed (see iaf_plan::last_stream).  Skipped while
+// either stream is being captured into a CUDA graph: a capture only ever sees one stream of ours.
+static int stream_handoff(iaf_plan* pl, cudaStream_t stream) {
+#ifndef IAF_EMU
+  if (pl->last_stream_valid && pl->last_stream != stream) {
+    cudaStreamCaptureStatus c0 = cudaStreamCaptureStatusNone, c1 = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(stream, &c1);
+    cudaStreamIsCapturing(pl->last_stream, &c0);
+    if (c0 == cudaStreamCaptureStatusNone && c1 == cudaStreamCaptureStatusNone) {
+      if (!pl->ev_handoff) CK(cudaEventCreateWithFlags(&pl->ev_handoff, cudaEventDisableTiming));
+      CK(cudaEventRecord(pl->ev_handoff, pl->last_stream));
+      CK(cudaStreamWaitEvent(stream, pl->ev_handoff, 0));
+    }
+  }
+  pl->last_stream = stream;
+  pl->last_stream_valid = true;
+#else
+  (void)pl; (void)stream;
+#endif
+  return IAF_OK;
 }
 
 static int ensure_scratch(iaf_plan* pl, int B) {
@@ -265,6 +292,7 @@ void iaf_plan_destroy(iaf_plan_t* pl) {
     if (pl->ev_cmp[i]) cudaEventDestroy(pl->ev_cmp[i]);
     if (pl->ev_d2h[i]) cudaEventDestroy(pl->ev_d2h[i]);
   }
+  if (pl->ev_handoff) cudaEventDestroy(pl->ev_handoff);
   if (pl->s_h2d) cudaStreamDestroy(pl->s_h2d);
   if (pl->s_cmp) cudaStreamDestroy(pl->s_cmp);
   if (pl->s_d2h) cudaStreamDestroy(pl->s_d2h);
@@ -281,6 +309,7 @@ int iaf_pack_weights(iaf_plan_t* pl, const float* const* w, const float* const* 
   const int n_layers = d.n_hidden + d.n_heads;
   for (int i = 0; i < n_layers; ++i)
     if (!w[i] || !scale[i] || !bias[i]) return IAF_ERR_BAD_ARG;
+  { int hs = stream_handoff(pl, stream); if (hs != IAF_OK) return hs; }
   IafPackParams pp;
   memset(&pp, 0, sizeof(pp));
   pp.n_layers = n_layers;
@@ -324,7 +353,10 @@ static int run(iaf_plan* pl, int mode, const float* z, const float* ctx, const f
                cudaStream_t stream, float* const* hid_out = nullptr) {
   if (!pl->packed) return IAF_ERR_NOT_PACKED;
   if (B <= 0) return IAF_ERR_BAD_ARG;
+  { int hs = stream_handoff(pl, stream); if (hs != IAF_OK) return hs; }
   const iaf_desc_t& d = pl->d;
+  // a plan the caller pinned to the tensor-core path never downgrades silently (see iaf_plan_path_for_entry)
+  if (pl->path == IAF_PATH_TC && pl->d.path == IAF_PATH_TC && !iaf_tc_mode_supported(pl->tc, mode)) return IAF_ERR_UNSUPPORTED;
   if (pl->path == IAF_PATH_TC && iaf_tc_mode_supported(pl->tc, mode)) {
     IafTcArgs a;
     memset(&a, 0, sizeof(a));
@@ -416,6 +448,7 @@ static int run_bwd(iaf_plan* pl, int mode, const float* z, const float* ctx, con
                    const float* logsd_saved = nullptr, const float* const* hidden_saved = nullptr) {
   if (!pl->packed) return IAF_ERR_NOT_PACKED;
   if (B <= 0) return IAF_ERR_BAD_ARG;
+  { int hs = stream_handoff(pl, stream); if (hs != IAF_OK) return hs; }
   const iaf_desc_t& d = pl->d;
   const int n_layers = d.n_hidden + d.n_heads;
   const bool want_params = g_w || g_scale || g_bias;
@@ -485,6 +518,7 @@ int iaf_layer_bwd(iaf_plan_t* pl, const float* eps, const float* post_mean, cons
   if (pl->d.n_heads != 2 || pl->d.head[0] != pl->d.n_z) return IAF_ERR_BAD_SHAPE;
   if (!pl->packed) return IAF_ERR_NOT_PACKED;
   if (B <= 0) return IAF_ERR_BAD_ARG;
+  { int hs = stream_handoff(pl, (cudaStream_t)stream); if (hs != IAF_OK) return hs; }
   const iaf_desc_t& d = pl->d;
   const bool want_params = g_w || g_scale || g_bias;
   if (want_params) {
@@ -652,6 +686,13 @@ int iaf_host_wait(iaf_plan_t* pl) {
 }
 
 int iaf_plan_path(const iaf_plan_t* pl) { return pl ? pl->path : IAF_ERR_BAD_ARG; }
+
+int iaf_plan_path_for_entry(const iaf_plan_t* pl, int entry) {
+  if (!pl || entry < IAF_MODE_MULTICONV || entry > IAF_MODE_LAYER) return IAF_ERR_BAD_ARG;
+  if (pl->path == IAF_PATH_TC && iaf_tc_mode_supported(pl->tc, entry)) return IAF_PATH_TC;
+  if (pl->path == IAF_PATH_TC && pl->d.path == IAF_PATH_TC) return IAF_ERR_UNSUPPORTED;
+  return pl->simt_ok ? IAF_PATH_SIMT : IAF_ERR_UNSUPPORTED;
+}
 uint64_t iaf_plan_launch_count(const iaf_plan_t* pl) { return pl ? pl->launches : 0; }
 
 size_t iaf_plan_algorithmic_bytes(const iaf_plan_t* pl, int B) {

@@ -1,7 +1,7 @@
 // Fused IAF step for stacks with ONE hidden layer (depth_ar = 1: BASELINE configs C1 / C2a), second generation.
 // Included by iaf_tc.cu (shares its PTX wrappers, parameter structs and the weight-prep kernel).
 //
-// Same formulation as iaf_tc_kernel (slot stream, tap = slot shift, bf16 hi/lo split operands, fp32 accumulation in
+// Same formulation as iaf_tc_kernel (slot stream, tap = slot shift, fp16 hi/lo split operands, fp32 accumulation in
 // TMEM), but a different schedule, designed around what bounded the first kernel (profiles/r1_c2a_ncu.md: every warp
 // stalled on the same global loads and the E0 -> M1 -> E0 chain through a two-tile ring):
 //
@@ -11,7 +11,7 @@
 //     in flight with two plain 128-slot h buffers (MIR / 128 = 14 % more stage-1 rows at 16x16).
 //   * WARP-SPECIALISED PRODUCERS.  All global LOADS of the hidden layer live in loader warps that run up to two tiles
 //     ahead of the pipeline and may stall as long as they like.  Per tile they
-//       - turn the fp32 z window into the bf16 hi/lo operand window in shared memory (layer mode: the posterior sample),
+//       - turn the fp32 z window into the fp16 hi/lo operand window in shared memory (layer mode: the posterior sample),
 //       - write context + bias (+ Theano pad-channel terms) INTO the stage-0 accumulator with tcgen05.st before the MMAs
 //         run, which then accumulate on top of it (accumulate = 1 from the first instruction; a loader warp is tied to
 //         its TMEM lane quadrant).  The hidden epilogue never touches global memory.
@@ -31,7 +31,8 @@
 #define FZ_W_LD0 FZ_EPI
 #define FZ_W_MMA (FZ_EPI + FZ_LD)
 #define FZ_W_RED (FZ_W_MMA + 1)
-#define FZ_THREADS ((FZ_W_RED + 1) * 32)
+#define FZ_W_TMA (FZ_W_MMA + 2)   // bulk-copy producer of the staged z window (idle in the gathered variant)
+#define FZ_THREADS ((FZ_W_TMA + 1) * 32)
 #define FZ_LTHREADS (FZ_LD * 32)
 #define FZ_ZB 3             // (slot, chunk) items of the z window per loader thread (FZ_ZB * loader threads >= items)
 #define FZ_CXG 2            // context channel groups (of 16) per loader warp (FZ_CXG * FZ_LGS * 16 >= hidden width)
@@ -51,7 +52,9 @@ enum {
   FB_A1_EMPTY = 17, // + b
   FB_PART = 19,     // + tile parity
   FB_PART_EMPTY = 21,
-  FB_COUNT = 23
+  FB_ZST_FULL = 23, // staged variant: the bulk copies of a tile's fp32 z rows have landed
+  FB_ZST_EMPTY = 24,// ... the loader warps have read them
+  FB_COUNT = 25
 };
 
 // Optional wait-time probe (compile with -DIAF_FZ_PROBE; development aid): the lead lane of each role in CTA 1 accumulates
@@ -75,6 +78,14 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// TMA tiled copy of one 4-D box (global -> shared), completing on an mbarrier
+__device__ __forceinline__ void tma_load_4d(void* dst, const void* tmap, int c0, int c1, int c2, int c3, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+      : "memory");
+}
 
 // Incremental slot decoding for the loaders: a thread's slots advance by TO per tile, so (sample n, offset r inside the
 // sample) is carried from tile to tile and only the row / column split is recomputed (one multiply-high).
@@ -93,9 +104,33 @@ __device__ __forceinline__ void advance_nr(const IafTcParams& p, int& n, int& r,
   while (r >= p.SPS) { r -= p.SPS; ++n; }
 }
 
+// Rows of the (at most two) samples a tile's z window touches, for the staged variant.  Stream slot s -> sample s / SPS,
+// offset r = s % SPS, stream row y = r / Wp (row H is the zero row and is never fetched).
+struct ZstGeo {
+  int n0, n1;        // samples (n1 = n0 + 1)
+  int y0, rows0;     // sample n0: first stream row in the window, number of image rows staged
+  int rows1;         // sample n1: image rows 0 .. rows1-1 staged
+};
+__device__ __forceinline__ ZstGeo zst_geometry(const IafTcParams& p, int s0) {
+  ZstGeo g;
+  g.n0 = fast_div(s0, p.SPS, p.mg_sps);
+  const int r0 = s0 - g.n0 * p.SPS;
+  g.y0 = fast_div(r0, p.Wp, p.mg_wp);
+  const int s1 = s0 + p.WIN - 1;
+  const int nb = fast_div(s1, p.SPS, p.mg_sps);
+  const int yb = min(p.H - 1, fast_div(s1 - nb * p.SPS, p.Wp, p.mg_wp));
+  g.n1 = g.n0 + 1;
+  const int ylast0 = (nb == g.n0) ? yb : p.H - 1;
+  g.rows0 = (g.n0 < p.B && g.y0 <= ylast0) ? ylast0 - g.y0 + 1 : 0;
+  g.rows1 = (nb > g.n0 && g.n1 < p.B) ? yb + 1 : 0;
+  return g;
+}
+
 template <bool PADW, int MODE, int NLT, int THW>
 __global__ void __launch_bounds__(FZ_THREADS, 1) iaf_fz_kernel(const __grid_constant__ IafTcParams p) {
   const int HW = THW ? THW : p.HW;
+  // staged variant: z reaches shared memory by bulk copies (the 16x16 instantiation, step / multiconv modes)
+  constexpr bool ZST = (THW == 256) && (MODE != IAF_MODE_LAYER);
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bars[FB_COUNT];
   __shared__ uint32_t s_tmem;
@@ -118,6 +153,8 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) iaf_fz_kernel(const __grid_cons
     tmem_alloc(&s_tmem, (uint32_t)p.tmem_cols);
     if (lane == 0) {
       mbar_init(&bars[FB_W], 1);
+      mbar_init(&bars[FB_ZST_FULL], 1);
+      mbar_init(&bars[FB_ZST_EMPTY], FZ_LD);
       for (int b = 0; b < 2; ++b) {
         mbar_init(&bars[FB_ZFULL + b], FZ_LD);
         mbar_init(&bars[FB_ZEMPTY + b], 1);
@@ -188,12 +225,14 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) iaf_fz_kernel(const __grid_cons
       if (k < nt) {
         // ---------------- M0(k): accumulates ON TOP of the context + bias the loader wrote ----------------
         const int b = k & 1;
+        const int zb = (p.nzw == 2) ? b : 0;                 // z operand window of tile k
+        const int zuse = (p.nzw == 2) ? (k >> 1) : k;        // how many times it has been filled before
         PROBE(7)
-        mbar_wait(&bars[FB_ZFULL + b], (uint32_t)((k >> 1) & 1));
+        mbar_wait(&bars[FB_ZFULL + zb], (uint32_t)(zuse & 1));
         PROBE(0)
         mbar_wait(&bars[FB_A0_INIT + b], (uint32_t)((k >> 1) & 1));
         PROBE(1)
-        const uint32_t a0h = a0h_0 + (uint32_t)b * zbuf_step, a0l = a0l_0 + (uint32_t)b * zbuf_step;
+        const uint32_t a0h = a0h_0 + (uint32_t)zb * zbuf_step, a0l = a0l_0 + (uint32_t)zb * zbuf_step;
         tc_fence_after();
         if (lane == 0) TL(0, 100, k);
         const uint32_t d = tmem_base + (uint32_t)(S0.tmem_col + b * S0.acc_cols);
@@ -210,13 +249,13 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) iaf_fz_kernel(const __grid_cons
 #pragma unroll 1
               for (int ks = 0; ks < nks0; ++ks) {
                 if (!mg0 || first) {
-                  umma_bf16(d, mk_desc(al), mk_desc(bh), idesc0, 1u);  // lo * hi
-                  umma_bf16(d, mk_desc(ah), mk_desc(bh), idesc0, 1u);  // hi * hi
+                  umma_f16(d, mk_desc(al), mk_desc(bh), idesc0, 1u);  // lo * hi
+                  umma_f16(d, mk_desc(ah), mk_desc(bh), idesc0, 1u);  // hi * hi
                   // hi * lo: own columns [N, 2N) when merged (nothing was written there: start from zero)
-                  umma_bf16(mg0 ? d + (uint32_t)S0.N : d, mk_desc(ah), mk_desc(bl), idesc0, mg0 ? 0u : 1u);
+                  umma_f16(mg0 ? d + (uint32_t)S0.N : d, mk_desc(ah), mk_desc(bl), idesc0, mg0 ? 0u : 1u);
                 } else {
-                  umma_bf16(d, mk_desc(ah), mk_desc(bh), idesc0m, 1u);  // hi * [hi | lo] as one N' = 2N instruction
-                  umma_bf16(d, mk_desc(al), mk_desc(bh), idesc0, 1u);
+                  umma_f16(d, mk_desc(ah), mk_desc(bh), idesc0m, 1u);  // hi * [hi | lo] as one N' = 2N instruction
+                  umma_f16(d, mk_desc(al), mk_desc(bh), idesc0, 1u);
                 }
                 first = false;
                 ah += a0_kstep; al += a0_kstep; bh += b0_kstep; bl += b0_kstep;
@@ -224,7 +263,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) iaf_fz_kernel(const __grid_cons
             }
           }
           umma_commit(&bars[FB_A0_FULL + b]);
-          umma_commit(&bars[FB_ZEMPTY + b]);
+          umma_commit(&bars[FB_ZEMPTY + zb]);
           TL(0, 200, k);
         }
         __syncwarp();
@@ -255,12 +294,12 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) iaf_fz_kernel(const __grid_cons
 #pragma unroll 1
               for (int ks = 0; ks < nks1; ++ks) {
                 if (mg1) {
-                  umma_bf16(d, mk_desc(ah), mk_desc(bh), idesc1m, acc);
-                  umma_bf16(d, mk_desc(al), mk_desc(bh), idesc1, 1u);
+                  umma_f16(d, mk_desc(ah), mk_desc(bh), idesc1m, acc);
+                  umma_f16(d, mk_desc(al), mk_desc(bh), idesc1, 1u);
                 } else {
-                  umma_bf16(d, mk_desc(al), mk_desc(bh), idesc1, acc);
-                  umma_bf16(d, mk_desc(ah), mk_desc(bl), idesc1, 1u);
-                  umma_bf16(d, mk_desc(ah), mk_desc(bh), idesc1, 1u);
+                  umma_f16(d, mk_desc(al), mk_desc(bh), idesc1, acc);
+                  umma_f16(d, mk_desc(ah), mk_desc(bl), idesc1, 1u);
+                  umma_f16(d, mk_desc(ah), mk_desc(bh), idesc1, 1u);
                 }
                 acc = 1;
                 ah += a1_kstep; al += a1_kstep; bh += b1_kstep; bl += b1_kstep;
@@ -279,7 +318,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) iaf_fz_kernel(const __grid_cons
   } else if (warp >= FZ_W_LD0 && warp < FZ_W_MMA) {
     // =====================================================================================
     // loader warps.  Per tile k, with every load of the tile in flight before the first wait:
-    //   (1) fp32 z window -> bf16 hi / lo operand window (layer mode: the posterior sample);
+    //   (1) fp32 z window -> fp16 hi / lo operand window (layer mode: the posterior sample);
     //   (2) accumulator b of stage 0 := context + bias (+ pad-channel terms)   (ar.py:402 / layers.py:163)
     // =====================================================================================
     const int lw = warp - FZ_W_LD0;
@@ -318,6 +357,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) iaf_fz_kernel(const __grid_cons
       const int b = k & 1;
       // ---- issue every global load of the tile first: z window items, then this warp's context channel groups ----
       float v[FZ_ZB][8];
+      if (!ZST) {
 #pragma unroll
       for (int it = 0; it < FZ_ZB; ++it) {
         if (z_dst[it] >= 0) {
@@ -339,6 +379,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) iaf_fz_kernel(const __grid_cons
           }
         }
       }
+      }
       const SlotInfo si = decode_nr(p, c_n, c_r, HW);
       advance_nr(p, c_n, c_r, TO);
       const bool bx0 = (si.x == 0), bxW = (si.x == p.W - 1), byH = (si.y == p.H - 1);
@@ -358,6 +399,42 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) iaf_fz_kernel(const __grid_cons
       }
       if (lw == 0 && lane == 0) TL(3, 41, k);
       PROBE(0)
+      if (ZST) {
+        // the tile's fp32 rows were staged by the TMA warp as [staged row][channel][x]: read this thread's items
+        // into registers and hand the staging buffer back BEFORE waiting for the operand window, so that the copies of
+        // tile k+1 are in flight while the MMAs of tile k-1 still own the window
+        const ZstGeo g = zst_geometry(p, (t0 + k) * TO);
+        mbar_wait(&bars[FB_ZST_FULL], (uint32_t)(k & 1));
+        const float* stg = reinterpret_cast<const float*>(smem + p.sm_zst);
+#pragma unroll
+        for (int it = 0; it < FZ_ZB; ++it) {
+          if (z_dst[it] >= 0) {
+            const SlotInfo zi = decode_nr(p, z_n[it], z_r[it], HW);
+            advance_nr(p, z_n[it], z_r[it], TO);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[it][e] = 0.f;
+            if (zi.valid && !(p.dbg & 1)) {
+              const bool second = zi.n != g.n0;
+              const int rows = second ? g.rows1 : g.rows0;
+              const int ylo = second ? 0 : g.y0;
+              const int rel = p.flip ? (ylo + rows - 1 - zi.y) : (zi.y - ylo);
+              const int xx = p.flip ? (p.W - 1 - zi.x) : zi.x;
+              const float* sp = stg + ((second ? g.rows0 : 0) + rel) * (p.C * p.W) + (z_cho[it] / HW) * p.W + xx;
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[it][e] = sp[e * p.W];
+            }
+          }
+        }
+        // the loads above must have returned before the buffer is released: make the arrive depend on their values
+        float dep = 0.f;
+#pragma unroll
+        for (int it = 0; it < FZ_ZB; ++it)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) dep += v[it][e];
+        __syncwarp();
+        if (lane == 0 || dep == 1.0e38f) mbar_arrive(&bars[FB_ZST_EMPTY]);
+      }
+      PROBE(6)
       if (!tables) {  // the bias tables travel with the weights
         mbar_wait(&bars[FB_W], 0);
         tables = true;
@@ -401,19 +478,21 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) iaf_fz_kernel(const __grid_cons
       if (lane == 0) mbar_arrive(&bars[FB_A0_INIT + b]);
       if (lw == 0 && lane == 0) TL(3, 40, k);
       PROBE(3)
-      // ---- (2) z window b (free once M0(k-2) has read it) ----
-      if (k >= 2) mbar_wait(&bars[FB_ZEMPTY + b], (uint32_t)(((k >> 1) - 1) & 1));
+      // ---- (2) z operand window ----
+      const int zb = (p.nzw == 2) ? b : 0;
+      const int zuse = (p.nzw == 2) ? (k >> 1) : k;
+      if (zuse >= 1) mbar_wait(&bars[FB_ZEMPTY + zb], (uint32_t)((zuse - 1) & 1));  // the M0 that read the window last
       PROBE(4)
 #pragma unroll
       for (int it = 0; it < FZ_ZB; ++it) {
         if (z_dst[it] >= 0 && !(p.dbg & 2)) {
-          uint8_t* dst = smem + S0.sm_in + b * p.z_bytes + z_dst[it];
+          uint8_t* dst = smem + S0.sm_in + zb * p.z_bytes + z_dst[it];
           split_store8(v[it], dst, dst + lo_off);
         }
       }
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars[FB_ZFULL + b]);
+      if (lane == 0) mbar_arrive(&bars[FB_ZFULL + zb]);
       if (lw == 0 && lane == 0) TL(2, 30, k);
       PROBE(5)
     }
@@ -434,12 +513,25 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) iaf_fz_kernel(const __grid_cons
     mbar_wait(&bars[FB_W], 0);  // the heads' bias table travels with the weights
     PROBE(6)
 
+    // this thread's slot advances by TO per tile: (sample, offset) carried incrementally; E1(k-1) reuses E0(k-1)'s decode
+    int e_n = fast_div(t0 * TO + sl, p.SPS, p.mg_sps);
+    int e_r = t0 * TO + sl - e_n * p.SPS;
+    int t_n = fast_div(t0 * TO, p.SPS, p.mg_sps);   // same for the tile's first slot
+    int t_r = t0 * TO - t_n * p.SPS;
+    SlotInfo si_prev;
+    si_prev.n = 0; si_prev.y = 0; si_prev.x = 0; si_prev.gp = 0; si_prev.valid = false;
+    int tn_prev = 0, tr_prev = 0;
     for (int k = 0; k <= nt; ++k) {
+      SlotInfo si_cur = si_prev;
+      int tn_cur = tn_prev, tr_cur = tr_prev;
       if (k < nt) {
         // ---------------- E0(k) ----------------
         const int b = k & 1;
-        const int u = t0 + k;
-        const SlotInfo si = decode_slot(p, u * TO + sl, HW);
+        const SlotInfo si = decode_nr(p, e_n, e_r, HW);
+        advance_nr(p, e_n, e_r, TO);
+        si_cur = si;
+        tn_cur = t_n; tr_cur = t_r;
+        advance_nr(p, t_n, t_r, TO);
         const uint32_t t_acc = t_lane + (uint32_t)(S0.tmem_col + b * S0.acc_cols);
         uint8_t* obase = smem + S1.sm_in + b * p.h_bytes + sl * 16;
         if (warp == 0 && lane == 0) TL(1, 9, k);
@@ -511,8 +603,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) iaf_fz_kernel(const __grid_cons
       if (k >= 1) {
         // ---------------- E1(k-1): columns in groups of 16 = (m x 8, s x 8) of 8 channels ----------------
         const int kk = k - 1, b = kk & 1;
-        const int u = t0 + kk;
-        const SlotInfo si = decode_slot(p, u * TO + sl, HW);
+        const SlotInfo si = si_prev;
         const bool act = si.valid && sl < TO;  // rows >= TO belong to the next tile (they only fed this tile's halo)
         const bool bx0 = (si.x == 0), bxW = (si.x == p.W - 1), byH = (si.y == p.H - 1);
         const uint32_t t_acc = t_lane + (uint32_t)(S1.tmem_col + b * S1.acc_cols);
@@ -520,10 +611,9 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) iaf_fz_kernel(const __grid_cons
         float red[NRED];
 #pragma unroll
         for (int i = 0; i < NRED; ++i) red[i] = 0.f;
-        const int tile_s0 = u * TO;
-        const int n_first = fast_div(tile_s0, p.SPS, p.mg_sps);
-        const int n_last = min(p.B - 1, fast_div(tile_s0 + TO - 1, p.SPS, p.mg_sps));
-        const int ns = (tile_s0 < p.S) ? (n_last - n_first + 1) : 0;
+        const int n_first = tn_prev;
+        const int n_last = min(p.B - 1, tn_prev + fast_div(tr_prev + TO - 1, p.SPS, p.mg_sps));
+        const int ns = (n_first < p.B) ? (n_last - n_first + 1) : 0;
         const int pb = kk & 1;  // partial-sum buffer
         const bool want_red = (MODE != IAF_MODE_MULTICONV) && (p.persample_out || p.bc_out);
         if (MODE == IAF_MODE_LAYER && want_red && kk >= 2)
@@ -652,8 +742,38 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) iaf_fz_kernel(const __grid_cons
           if (lane == 0) mbar_arrive(&bars[FB_PART + pb]);
         }
       }
+      si_prev = si_cur; tn_prev = tn_cur; tr_prev = tr_cur;
     }
     if (warp == 0) { PROBE_DUMP(2) }
+  } else if (ZST && warp == FZ_W_TMA) {
+    // =====================================================================================
+    // TMA producer (staged variant): the fp32 rows of z a tile's window touches -> staging buffer, as tiled tensor
+    // copies (cp.async.bulk.tensor.4d over z viewed as (x, y, channel, sample)): one box = one image row of every
+    // channel, <= 10 boxes per tile, issued by the warp's lanes in parallel and completing on one mbarrier (expect_tx).
+    // (Per-(sample, channel) 1-D bulk copies were measured first: 64 copies of <= 640 B per tile cost ~3 K cycles of TMA
+    //  issue per tile and made this variant slower than the gathered one.)
+    // =====================================================================================
+    uint8_t* stg = smem + p.sm_zst;
+    const uint32_t row_bytes = (uint32_t)(p.C * p.W * 4);
+    // (L2 prefetch of the rows of the tiles further ahead -- cp.async.bulk.prefetch.tensor for z and for the context --
+    //  was measured: 26.8 us against 25.0 us without; the extra descriptor-based requests delay the copies themselves.)
+    for (int k = 0; k < nt; ++k) {
+      const ZstGeo g = zst_geometry(p, (t0 + k) * TO);
+      if (k >= 1) mbar_wait(&bars[FB_ZST_EMPTY], (uint32_t)((k - 1) & 1));
+      const int nrows = g.rows0 + g.rows1;
+      if (lane == 0) mbar_expect_tx(&bars[FB_ZST_FULL], (p.dbg & 1) ? 0u : (uint32_t)nrows * row_bytes);
+      __syncwarp();
+      if (!(p.dbg & 1) && lane < nrows) {
+        // lane r fetches staged row r: box (x 0..W-1, one image row, every channel, one sample) = C * W floats.
+        // First staged memory row of each sample (Theano orientation: the stream is the point-reflected image)
+        const int m0 = p.flip ? p.H - g.y0 - g.rows0 : g.y0;
+        const int m1 = p.flip ? p.H - g.rows1 : 0;
+        const bool second = lane >= g.rows0;
+        const int row = second ? m1 + (lane - g.rows0) : m0 + lane;
+        tma_load_4d(stg + (size_t)lane * row_bytes, p.tmap_z, 0, row, 0, second ? g.n1 : g.n0, &bars[FB_ZST_FULL]);
+      }
+      __syncwarp();
+    }
   } else if (warp == FZ_W_RED && (p.persample_out || p.bc_out) && MODE != IAF_MODE_MULTICONV) {
     // =====================================================================================
     // reducer warp: per-tile partials -> per-sample outputs (a sample's last tile sums all of its tiles in fixed order)

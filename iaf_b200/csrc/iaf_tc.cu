@@ -15,8 +15,8 @@
 //
 // Precision.  north_star asks for 1e-4 relative parity with the fp32 reference; bf16 (or
 // tf32) single-pass operands cannot hold that through K = 160..800 and the 8192-element
-// log-det sum (SURVEY hard part 1).  Operands are therefore split x = hi + lo (both bf16,
-// 16 significant bits together) and three MMAs are issued per K block:
+// log-det sum (SURVEY hard part 1).  Operands are therefore split x = hi + lo (both fp16,
+// 22 significant bits together; see umma_idesc) and three MMAs are issued per K block:
 // hi*hi + lo*hi + hi*lo, fp32 accumulation in TMEM.  Roofline numbers are always quoted
 // on ALGORITHMIC flops, not on the 3x issued.
 //
@@ -29,7 +29,9 @@
 // margin (so a shifted 128-row window never wraps), and every hand-off is an mbarrier
 // (TMA-style expect_tx for the weights, tcgen05.commit for MMA completion).
 // Orientation of the Theano variant: see iaf_simt.cu (point reflection on load/store).
+#include <cuda.h>  // CUtensorMap (the encoder is fetched through cudaGetDriverEntryPoint: no link-time libcuda dependency)
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -89,6 +91,9 @@ struct IafTcStage {
 };
 
 struct IafTcParams {
+  // iaf_fz_kernel, staged variant: TMA descriptor of z viewed as a 4-D tensor (x, y, channel, sample), box = one image
+  // row of every channel; 64-byte aligned as the hardware requires of a descriptor passed in kernel-parameter space
+  alignas(64) unsigned char tmap_z[128];
   const float* z; const float* ctx;
   const float* post_mean; const float* post_logsd; const float* prior_mean; const float* prior_logsd;
   float* z_out; float* elem; float* bc_out; float* persample_out;
@@ -114,6 +119,8 @@ struct IafTcParams {
   int TO;        // output slots per tile (128 - MIR)
   int h_bytes;   // bytes of one hidden-activation operand buffer (hi + lo plane sets of 128 slots)
   int z_bytes;   // bytes of one z operand window (hi + lo plane sets of WIN slots, rounded up to 128)
+  int nzw;       // z operand windows: 2 (loaders a full tile ahead) or 1
+  int sm_zst;    // byte offset of the fp32 z staging buffer the bulk copies land in (staged variant, 16x16 planes)
   int dbg;       // IAF_FZ_DBG (development, timing only, results WRONG when set): 1 loaders issue no global loads,
                  // 2 loaders also skip their stores, 4 E0 does nothing but the hand-off, 8 E1 likewise, 16 no MMAs, 32 no weight load
 };
@@ -171,8 +178,8 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 x bf16 -> f32
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[smem desc] * B[smem desc], 16-bit operands (formats in the instruction descriptor) -> f32
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
@@ -202,9 +209,14 @@ __device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr, uint32_t lbo_by
 }
 #define UMMA_DESC_HI ((128u >> 4) | (1u << 14))
 __device__ __forceinline__ uint64_t mk_desc(uint32_t lo) { return ((uint64_t)UMMA_DESC_HI << 32) | lo; }
-// Instruction descriptor (InstrDescriptor): f32 accumulate, A/B bf16, both K-major, M=128.
+// Instruction descriptor (InstrDescriptor): f32 accumulate, A and B fp16 (a_format bits [7,10), b_format bits [10,13):
+// 0 = f16, 1 = bf16), both K-major, M=128.  Why fp16 pairs and not bf16 pairs: the residual of a two-term WEIGHT split
+// is the same for every pixel and so adds up coherently over the 8192 elements of a sample's log-det (bf16 + bf16 leaves
+// 2^-17 |w|: ~2e-4 absolute, measured on the B200 against the fp64 oracle over all 256 samples; fp16 + fp16 leaves
+// 2^-23 |w|).  Weight-normalised weights are bounded by their gain (|w| <= exp(g), exp(3s)); see split_store8 for the
+// activations' range.
 __device__ __forceinline__ uint32_t umma_idesc(int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_TILE >> 4) << 24);
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_TILE >> 4) << 24);
 }
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -257,21 +269,21 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-// split 8 floats into bf16 hi / lo and store both 16-byte vectors
+// split 8 floats into fp16 hi / lo (22 significant bits together) and store both 16-byte vectors.  fp16, not bf16: the
+// a_lo * w_lo product the three-MMA scheme drops and the residual of the two-term split both shrink 64x (CPU simulation
+// tools/experiments/prec_sim.py: worst per-sample log-det error on C2a 1.3e-4 with bf16 pairs, 5e-6 with fp16 pairs).
+// Range: |x| >= 65520 becomes inf and the step's outputs NaN (loud, never silently wrong); values below 6e-5 keep an
+// absolute resolution of 3e-8.
 __device__ __forceinline__ void split_store8(const float* v, uint8_t* hi_ptr, uint8_t* lo_ptr) {
   uint32_t h[4], l[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-    const uint32_t hb = *reinterpret_cast<const uint32_t*>(&hh);
-#ifdef TC_FAST_EPI
+    const __half2 hh = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    const float2 hf = __half22float2(hh);
     float r0 = v[2 * i], r1 = v[2 * i + 1];
-    sub2(r0, r1, __uint_as_float(hb << 16), __uint_as_float(hb & 0xFFFF0000u));
-#else
-    const float r0 = v[2 * i] - __uint_as_float(hb << 16), r1 = v[2 * i + 1] - __uint_as_float(hb & 0xFFFF0000u);
-#endif
-    const __nv_bfloat162 ll = __floats2bfloat162_rn(r0, r1);
-    h[i] = hb;
+    sub2(r0, r1, hf.x, hf.y);
+    const __half2 ll = __floats2half2_rn(r0, r1);
+    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
     l[i] = *reinterpret_cast<const uint32_t*>(&ll);
   }
   *reinterpret_cast<uint4*>(hi_ptr) = make_uint4(h[0], h[1], h[2], h[3]);
@@ -473,12 +485,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
             for (int ks = 0; ks < nks; ++ks) {
               if (merged) {
                 // hi * [hi | lo] as one N' = 2N instruction (A fetched once for both), then lo * hi into the hi half
-                umma_bf16(d_tmem, mk_desc(ah), mk_desc(bh), idesc2, acc);
-                umma_bf16(d_tmem, mk_desc(al), mk_desc(bh), idesc, 1u);
+                umma_f16(d_tmem, mk_desc(ah), mk_desc(bh), idesc2, acc);
+                umma_f16(d_tmem, mk_desc(al), mk_desc(bh), idesc, 1u);
               } else {
-                umma_bf16(d_tmem, mk_desc(al), mk_desc(bh), idesc, acc);  // lo * hi
-                umma_bf16(d_tmem, mk_desc(ah), mk_desc(bl), idesc, 1u);   // hi * lo
-                umma_bf16(d_tmem, mk_desc(ah), mk_desc(bh), idesc, 1u);   // hi * hi
+                umma_f16(d_tmem, mk_desc(al), mk_desc(bh), idesc, acc);  // lo * hi
+                umma_f16(d_tmem, mk_desc(ah), mk_desc(bl), idesc, 1u);   // hi * lo
+                umma_f16(d_tmem, mk_desc(ah), mk_desc(bh), idesc, 1u);   // hi * hi
               }
               acc = 1;
               ah += a_kstep; al += a_kstep; bh += b_kstep; bl += b_kstep;
@@ -1081,8 +1093,12 @@ __global__ void __launch_bounds__(128) iaf_tc_pack_kernel(const __grid_constant_
       v *= factor;
       // K order: fused kernel [tap][ci]; layer-at-a-time kernel [ci / 16][tap][ci % 16]
       const int k = p.korder ? (((ci >> 4) * IAF_NTAPS + t) * 16 + (ci & 15)) : (t * L.cin + ci);
-      const __nv_bfloat16 h = __float2bfloat16_rn(v);
-      const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+      // fp16 hi + fp16 lo (22 significant bits); saturated at the fp16 range (a gain of e^11 is not a weight-norm layer)
+      const float vc = fminf(fmaxf(v, -65000.f), 65000.f);
+      const __half hh = __float2half_rn(vc);
+      const __half lh = __float2half_rn(vc - __half2float(hh));
+      const __nv_bfloat16 h = __ushort_as_bfloat16(__half_as_ushort(hh));  // raw 16-bit patterns travel in the bf16-typed images
+      const __nv_bfloat16 l = __ushort_as_bfloat16(__half_as_ushort(lh));
       if (p.korder) {  // layered kernel: separate hi / lo images [K/8][N][8]
         const size_t o = ((size_t)(k >> 3) * L.N + col) * 8 + (k & 7);
         L.whi[o] = h;
@@ -1118,6 +1134,9 @@ struct IafTcPlan {
   // second-generation fused kernel (iaf_fz_kernel: exactly one hidden layer)
   bool fz;
   int TO, h_bytes, z_bytes;
+  // the kernel has two shared-memory layouts: [0] z gathered by the loader warps (two operand windows when they fit),
+  // [1] z staged by bulk copies (one operand window + an fp32 staging buffer; 16x16 planes, step / multiconv modes)
+  struct FzLay { bool ok, layer_ok; int nzw, sm_zst, sm_in1, sm_bias[2], sm_part; size_t smem; } fzl[2];
   // layer-at-a-time mode (hidden widths that do not fit the fused kernel's on-chip rings)
   bool layered;
   int ly_stage[IAF_MAX_STAGES];
@@ -1170,6 +1189,42 @@ static LyKernel ly_kernel_for(bool padw, int mode, bool elu, int hw) {
   return hw == 256 ? ly_kernel_pick<256>(padw, mode, elu) : ly_kernel_pick<0>(padw, mode, elu);
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry-point lookup
+typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TmapEncodeFn tmap_encoder() {
+  static TmapEncodeFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<TmapEncodeFn>(ptr);
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+// z [B][C][H][W] fp32 as (x, y, c, n); box = (W, 1, C, 1): one image row of every channel of one sample (C * W * 4 bytes)
+static bool encode_z_tmap(unsigned char* out128, const float* z, int B, int C, int H, int W) {
+  TmapEncodeFn enc = tmap_encoder();
+  if (!enc) return false;
+  CUtensorMap tm;
+  const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
+  const cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)C * H * W * 4};
+  const cuuint32_t box[4] = {(cuuint32_t)W, 1u, (cuuint32_t)C, 1u};
+  const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(z), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return false;
+  static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap is 128 bytes");
+  memcpy(out128, &tm, 128);
+  return true;
+}
+
 template <int THW>
 static TcKernel fz_kernel_pick(bool padw, int mode, bool elu) {
   if (mode == IAF_MODE_MULTICONV) {
@@ -1183,8 +1238,10 @@ static TcKernel fz_kernel_pick(bool padw, int mode, bool elu) {
   if (padw) return elu ? iaf_fz_kernel<true, IAF_MODE_LAYER, IAF_NL_ELU, THW> : iaf_fz_kernel<true, IAF_MODE_LAYER, -1, THW>;
   return elu ? iaf_fz_kernel<false, IAF_MODE_LAYER, IAF_NL_ELU, THW> : iaf_fz_kernel<false, IAF_MODE_LAYER, -1, THW>;
 }
-static TcKernel fz_kernel_for(bool padw, int mode, bool elu, int hw) {
-  return hw == 256 ? fz_kernel_pick<256>(padw, mode, elu) : fz_kernel_pick<0>(padw, mode, elu);
+// the compile-time-plane instantiation (THW = 256) is used for 16x16 planes only: it is also the one whose step /
+// multiconv modes stage z with bulk copies
+static TcKernel fz_kernel_for(bool padw, int mode, bool elu, bool plane256) {
+  return plane256 ? fz_kernel_pick<256>(padw, mode, elu) : fz_kernel_pick<0>(padw, mode, elu);
 }
 
 static int tc_round_up(int a, int b) { return (a + b - 1) / b * b; }
@@ -1218,24 +1275,43 @@ static bool fz_layout(const iaf_desc_t* d, IafTcPlan* pl) {
   q->in_slots[0] = q->WIN;
   q->sm_in[0] = off;
   q->z_bytes = tc_round_up(2 * (q->cin[0] / 8) * q->WIN * 16, 128);
-  off += 2 * q->z_bytes;  // two z windows: the loaders run a full tile ahead of the MMAs
   if ((q->cin[0] / 8) * q->WIN > FZ_ZB * FZ_LTHREADS || q->N[0] > 16 * FZ_CXG * FZ_LGS) return false;
   q->in_slots[1] = TC_TILE;
-  q->sm_in[1] = off;
   q->h_bytes = 2 * (q->cin[1] / 8) * TC_TILE * 16;
-  off += 2 * q->h_bytes;
-  off += tc_round_up(MIR * 16, 128);  // a shifted 128-row window of the last plane reads MIR rows past the buffer
-  for (int j = 0; j < 2; ++j) {
-    q->sm_bias[j] = off;
-    off += 5 * q->N[j] * 4;
-  }
-  off = tc_round_up(off, 16);
-  q->sm_part = off;
+  if (q->MAXS > 32) return false;  // the reducer warp keeps one per-sample value per lane (8 in layer mode)
   const int part_step = 2 * FZ_EPI * q->MAXS * 4;
   const int part_layer = 2 * 4 * q->MAXS * d->n_z * 4;
-  if (q->MAXS > 32) return false;  // the reducer warp keeps one per-sample value per lane ...
-  q->layer_ok = (off + std::max(part_step, part_layer)) <= TC_SMEM_LIMIT && q->MAXS * d->n_z <= 256;  // ... 8 in layer mode
-  off += q->layer_ok ? std::max(part_step, part_layer) : part_step;
+  const int zoff = off;
+  bool any = false;
+  for (int v = 0; v < 2; ++v) {
+    IafTcPlan::FzLay& L = q->fzl[v];
+    L.ok = false;
+    // staged: 16x16 planes only (the kernel's compile-time-plane instantiation is the staged one)
+    if (v == 1 && !(d->H == 16 && d->W == 16 && d->n_z <= 32 && tmap_encoder())) continue;
+    for (int nzw = (v == 1 ? 1 : 2); nzw >= 1 && !L.ok; --nzw) {
+      int o = zoff + nzw * q->z_bytes;
+      L.nzw = nzw;
+      L.sm_zst = o;
+      if (v == 1) {
+        const int rows = (q->WIN + Wp - 2) / Wp + 1;  // stream rows a window can touch
+        o += tc_round_up(d->n_z * rows * d->W * 4, 128);
+      }
+      L.sm_in1 = o;
+      o += 2 * q->h_bytes;
+      o += tc_round_up(MIR * 16, 128);  // a shifted 128-row window of the last plane reads MIR rows past the buffer
+      for (int j = 0; j < 2; ++j) { L.sm_bias[j] = o; o += 5 * q->N[j] * 4; }
+      o = tc_round_up(o, 16);
+      L.sm_part = o;
+      L.layer_ok = v == 0 && (o + std::max(part_step, part_layer)) <= TC_SMEM_LIMIT && q->MAXS * d->n_z <= 256;
+      o += L.layer_ok ? std::max(part_step, part_layer) : part_step;
+      L.smem = (size_t)o;
+      L.ok = o <= TC_SMEM_LIMIT;
+    }
+    any = any || L.ok;
+  }
+  if (!q->fzl[0].ok) return false;  // the gathered variant serves every mode; the staged one is an extra
+  q->layer_ok = q->fzl[0].layer_ok;
+  q->smem = std::max(q->fzl[0].smem, q->fzl[1].ok ? q->fzl[1].smem : (size_t)0);
   // TMEM: both accumulators double-buffered; what is left goes to the merged hi*[hi|lo] form, the heads first
   int cols = 2 * (q->N[0] + q->N[1]);
   if (cols > 512) return false;
@@ -1249,8 +1325,7 @@ static bool fz_layout(const iaf_desc_t* d, IafTcPlan* pl) {
   int tc = 32;
   while (tc < col) tc *= 2;
   q->tmem_cols = tc;
-  q->smem = (size_t)off;
-  return off <= TC_SMEM_LIMIT;
+  return true;
 }
 
 static bool tc_layout(const iaf_desc_t* d, IafTcPlan* pl) {
@@ -1399,9 +1474,10 @@ int iaf_tc_plan_create(IafTcPlan** out, const iaf_desc_t* d) {
   for (int a = 0; a < 12; ++a) {
     cudaError_t e;
     const int md = (a >> 2) == 0 ? IAF_MODE_MULTICONV : ((a >> 2) == 1 ? IAF_MODE_STEP : IAF_MODE_LAYER);
-    if (pl->fz)
-      e = iaf_smem_optin(fz_kernel_for(a & 1, md, a & 2, d->H * d->W));
-    else if (pl->layered)
+    if (pl->fz) {
+      e = iaf_smem_optin(fz_kernel_for(a & 1, md, a & 2, false));
+      if (e == cudaSuccess) e = iaf_smem_optin(fz_kernel_for(a & 1, md, a & 2, true));
+    } else if (pl->layered)
       e = iaf_smem_optin(ly_kernel_for(a & 1, md, a & 2, d->H * d->W));
     else
       e = iaf_smem_optin(tc_kernel_for(a & 1, md, a & 2, d->H * d->W));
@@ -1494,10 +1570,29 @@ extern "C" void iaf_fz_probe_dump(void) {
   for (int r = 0; r < 3; ++r) {
     long long tot = 0;
     for (int i = 0; i < 8; ++i) tot += h[r][i];
+    if (!tot) continue;
     printf("PROBE %-16s total %7lld :", roles[r], tot);
     for (int i = 0; i < 8; ++i) printf("  %s %lld", names[r][i], h[r][i]);
     printf("\n");
   }
+  // layer-at-a-time kernel: [stage][role][slot]
+  long long g[4][3][8];
+  cudaMemcpyFromSymbol(g, g_ly_probe, sizeof(g));
+  static const char* lnames[3][4] = {{"wait ring slot free", "issue copies", "-", "-"},
+                                     {"wait ACC_EMPTY", "wait A window", "wait ring stage", "issue MMAs + glue"},
+                                     {"wait ACC_FULL", "pre-wait (context / z loads)", "epilogue body", "z window build"}};
+  static const char* lroles[3] = {"producer", "MMA warp", "worker warp 0"};
+  for (int st = 0; st < 4; ++st)
+    for (int r = 0; r < 3; ++r) {
+      long long tot = 0;
+      for (int i = 0; i < 8; ++i) tot += g[st][r][i];
+      if (!tot) continue;
+      printf("PROBE layered stage %d %-14s total %7lld :", st, lroles[r], tot);
+      for (int i = 0; i < 4; ++i) printf("  %s %lld", lnames[r][i], g[st][r][i]);
+      printf("\n");
+    }
+  static long long zero[4][3][8];
+  cudaMemcpyToSymbol(g_ly_probe, zero, sizeof(zero));
 }
 #endif
 
@@ -1568,6 +1663,21 @@ int iaf_tc_run(IafTcPlan* pl, const IafTcArgs* a, cudaStream_t stream, int* n_la
   p.mg_wp = (unsigned)((1ULL << 32) / (unsigned)p.Wp) + 1u;
   p.mg_win = (unsigned)((1ULL << 32) / (unsigned)p.WIN) + 1u;
   p.TO = pl->TO; p.h_bytes = pl->h_bytes; p.z_bytes = pl->z_bytes;
+  size_t fz_smem = 0;
+  bool fz_plane256 = false;
+  if (pl->fz) {
+    // staged z (bulk copies) when the plan has that layout and the mode allows it; IAF_FZ_STAGE=0 switches it off (A/B)
+    const char* st = getenv("IAF_FZ_STAGE");
+    bool staged = pl->fzl[1].ok && a->mode != IAF_MODE_LAYER && !(st && st[0] == '0');
+    // the descriptor carries the z pointer, so it is encoded per call (host side, ~1 us) and travels in the parameters
+    if (staged && ((reinterpret_cast<uintptr_t>(a->z) & 15) != 0 || !encode_z_tmap(p.tmap_z, a->z, B, d.n_z, d.H, d.W))) staged = false;
+    fz_plane256 = d.H == 16 && d.W == 16 && (staged || a->mode == IAF_MODE_LAYER);
+    const IafTcPlan::FzLay& L = pl->fzl[staged ? 1 : 0];
+    p.nzw = L.nzw; p.sm_zst = L.sm_zst; p.sm_part = L.sm_part;
+    p.st[1].sm_in = L.sm_in1;
+    p.st[0].sm_bias = L.sm_bias[0]; p.st[1].sm_bias = L.sm_bias[1];
+    fz_smem = L.smem;
+  }
   { const char* dbg = getenv("IAF_FZ_DBG"); p.dbg = dbg ? atoi(dbg) : 0; }
   const int grid = std::min(pl->num_sms, NT);
   if (pl->layered) {
@@ -1586,6 +1696,7 @@ int iaf_tc_run(IafTcPlan* pl, const IafTcArgs* a, cudaStream_t stream, int* n_la
       q.o_lo = pl->img[j & 1][1];
       q.S_pad = pl->img_S_pad;
       q.in_mode = j ? 1 : 0;
+      q.stage_id = j;
       q.first = j == 0;
       q.is_heads = j == pl->n_stages - 1;
       q.NB = pl->ly_NB[j];
@@ -1623,13 +1734,14 @@ int iaf_tc_run(IafTcPlan* pl, const IafTcArgs* a, cudaStream_t stream, int* n_la
     if (n_launches) *n_launches = pl->n_stages;
     return cudaGetLastError() == cudaSuccess ? IAF_OK : IAF_ERR_CUDA;
   }
-  TcKernel k = pl->fz ? fz_kernel_for(d.variant == IAF_VARIANT_THEANO, a->mode, d.nl == IAF_NL_ELU, d.H * d.W)
+  TcKernel k = pl->fz ? fz_kernel_for(d.variant == IAF_VARIANT_THEANO, a->mode, d.nl == IAF_NL_ELU, fz_plane256)
                       : tc_kernel_for(d.variant == IAF_VARIANT_THEANO, a->mode, d.nl == IAF_NL_ELU, d.H * d.W);
   {
     const char* e = getenv("IAF_PDL");
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(pl->fz ? FZ_THREADS : TC_THREADS); cfg.dynamicSmemBytes = pl->smem;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(pl->fz ? FZ_THREADS : TC_THREADS);
+    cfg.dynamicSmemBytes = pl->fz ? fz_smem : pl->smem;
     cfg.stream = stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

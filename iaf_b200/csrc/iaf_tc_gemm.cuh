@@ -16,6 +16,19 @@
 // tile i+1.
 #pragma once
 
+// Optional wait-time probe of the layer-at-a-time kernel (-DIAF_FZ_PROBE, development aid; see iaf_fz.cuh): CTA 1's lead
+// lanes accumulate the cycles spent per wait / phase; g_ly_probe[stage][role][slot].
+#ifdef IAF_FZ_PROBE
+__device__ long long g_ly_probe[4][3][8];
+#define LPROBE_DECL long long lpr_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long lpt_ = clock64();
+#define LPROBE(slot) { const long long n_ = clock64(); lpr_[slot] += n_ - lpt_; lpt_ = n_; }
+#define LPROBE_DUMP(role) if (blockIdx.x == 1 && lane == 0) { for (int i_ = 0; i_ < 8; ++i_) g_ly_probe[q.stage_id & 3][role][i_] = lpr_[i_]; }
+#else
+#define LPROBE_DECL
+#define LPROBE(slot)
+#define LPROBE_DUMP(role)
+#endif
+
 #define LY_WORKERS 16
 #define LY_WTHREADS (LY_WORKERS * 32)
 #define LY_MMA_WARP LY_WORKERS
@@ -75,6 +88,7 @@ struct IafLyParams {
   int n_bchunks;               // weight chunks per tile
   int tl_enable;               // timeline builds only: this launch flushes its events
   int cs;                      // cluster size (1, 2 or 4): CTAs sharing the weight stream by TMA multicast
+  int stage_id;                // which conv stage of the stack this launch is (probe / timeline builds)
 };
 
 template <bool PADW, int MODE, int NLT, int THW>
@@ -144,6 +158,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) iaf_ly_kernel(const __grid_cons
     // ===================== producer: A windows (operand-image input) and the weight ring =====================
     if (lane == 0) {
       int gchunk = 0;
+      LPROBE_DECL
       for (int i = 0; i < n_my; ++i) {
         const int u = (int)blockIdx.x + i * (int)gridDim.x;
         // K order is [K-step within a tap][tap]: weight chunk c and A chunk pair (2c, 2c+1) are consumed together,
@@ -152,7 +167,9 @@ __global__ void __launch_bounds__(LY_THREADS, 1) iaf_ly_kernel(const __grid_cons
           if (resident && i >= 1 && !q.in_mode) continue;  // weights already resident, A comes from the workers
           const int stg = gchunk % q.NB;
           const int use = gchunk / q.NB;
+          LPROBE(1)
           if (use >= 1) mbar_wait(&bars[LB_BEMPTY + stg], (uint32_t)((use - 1) & 1));
+          LPROBE(0)
           uint8_t* dst = smem + q.sm_b + stg * q.stage_bytes;
           const size_t bo = (size_t)c * q.b_chunk_bytes;
           const bool real = u < p.NT;
@@ -186,6 +203,8 @@ __global__ void __launch_bounds__(LY_THREADS, 1) iaf_ly_kernel(const __grid_cons
           ++gchunk;
         }
       }
+      LPROBE(1)
+      LPROBE_DUMP(0)
     }
     __syncwarp();
   } else if (warp == LY_MMA_WARP) {
@@ -199,17 +218,23 @@ __global__ void __launch_bounds__(LY_THREADS, 1) iaf_ly_kernel(const __grid_cons
     const uint32_t ah_base = umma_desc_lo(a_base, (uint32_t)a_plane);
     const uint32_t al_base = umma_desc_lo(a_base + (uint32_t)a_lo_off, (uint32_t)a_plane);
     int gchunk = 0;
+    LPROBE_DECL
     for (int i = 0; i < n_my; ++i) {
       const int b = i & 1, use = i >> 1;
+      LPROBE(3)
       if (use >= 1) mbar_wait(&bars[LB_ACC_EMPTY + b], (uint32_t)((use - 1) & 1));
+      LPROBE(0)
       tc_fence_after();
       if (lane == 0) TL(0, 100, i);
       const uint32_t d_tmem = tmem_base + (uint32_t)(b * acc_cols);
       for (int c = 0; c < q.n_bchunks; ++c) {
         const bool res = resident && !q.in_mode;
         const int stg = res ? c : gchunk % q.NB;
+        LPROBE(3)
         if (!q.in_mode) mbar_wait(&bars[LB_AFULL + c], (uint32_t)(i & 1));
+        LPROBE(1)
         mbar_wait(&bars[LB_BFULL + stg], res ? 0u : (uint32_t)((gchunk / q.NB) & 1));
+        LPROBE(2)
         tc_fence_after();
         const uint32_t sbase = smem_u32(smem + q.sm_b + stg * q.stage_bytes);
         uint32_t ah0, al0, bbase;
@@ -227,9 +252,9 @@ __global__ void __launch_bounds__(LY_THREADS, 1) iaf_ly_kernel(const __grid_cons
         const uint32_t acc0 = c ? 1u : 0u;
         if (elect_one_sync()) {
 #define LY_TAP(T, SH, ACC)                                                                   \
-          umma_bf16(d_tmem, mk_desc(al0 + (SH)), mk_desc(bh0 + (T) * b_tstep), idesc, (ACC)); \
-          umma_bf16(d_tmem, mk_desc(ah0 + (SH)), mk_desc(bl0 + (T) * b_tstep), idesc, 1u);    \
-          umma_bf16(d_tmem, mk_desc(ah0 + (SH)), mk_desc(bh0 + (T) * b_tstep), idesc, 1u);
+          umma_f16(d_tmem, mk_desc(al0 + (SH)), mk_desc(bh0 + (T) * b_tstep), idesc, (ACC)); \
+          umma_f16(d_tmem, mk_desc(ah0 + (SH)), mk_desc(bl0 + (T) * b_tstep), idesc, 1u);    \
+          umma_f16(d_tmem, mk_desc(ah0 + (SH)), mk_desc(bh0 + (T) * b_tstep), idesc, 1u);
           LY_TAP(0u, 0u, acc0)
           LY_TAP(1u, sh1, 1u)
           LY_TAP(2u, sh2, 1u)
@@ -250,6 +275,8 @@ __global__ void __launch_bounds__(LY_THREADS, 1) iaf_ly_kernel(const __grid_cons
         if (!res) ++gchunk;
       }
     }
+    LPROBE(3)
+    LPROBE_DUMP(1)
   } else if (warp < LY_WORKERS) {
     // ===================== workers: (first stage) z -> operand window; epilogues =====================
     const int qd = warp & 3, cg = warp >> 2;
@@ -304,9 +331,12 @@ __global__ void __launch_bounds__(LY_THREADS, 1) iaf_ly_kernel(const __grid_cons
         for (int c = 0; c < q.n_bchunks; ++c) mbar_arrive(&bars[LB_AFULL + c]);
     };
 
+    LPROBE_DECL
     if (!q.in_mode && n_my > 0) load_window(0);
     for (int i = 0; i < n_my; ++i) {
+      LPROBE(2)
       if (!q.in_mode && i + 1 < n_my) load_window(i + 1);
+      LPROBE(3)
       const int u = (int)blockIdx.x + i * (int)gridDim.x;
       const int b = i & 1, use = i >> 1;
       const SlotInfo si = decode_slot(p, u * TC_TILE + sl, HW);
@@ -336,8 +366,10 @@ __global__ void __launch_bounds__(LY_THREADS, 1) iaf_ly_kernel(const __grid_cons
           for (int e = 0; e < 16; ++e) cx[e] = cxn[e];
           fetch_ctx(g + CGS);
           if (!waited) {
+            LPROBE(1)
             mbar_wait(&bars[LB_ACC_FULL + b], (uint32_t)(use & 1));
             tc_fence_after();
+            LPROBE(0)
             waited = true;
             if (warp == 0 && lane == 0) TL(1, 50, i);
           }
@@ -448,8 +480,10 @@ __global__ void __launch_bounds__(LY_THREADS, 1) iaf_ly_kernel(const __grid_cons
             for (int e = 0; e < 8; ++e) zv[e] = __ldg(p.z + gi + (size_t)e * HW);
           }
           if (!waited) {
+            LPROBE(1)
             mbar_wait(&bars[LB_ACC_FULL + b], (uint32_t)(use & 1));
             tc_fence_after();
+            LPROBE(0)
             waited = true;
             if (warp == 0 && lane == 0) TL(1, 50, i);
           }
@@ -534,6 +568,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) iaf_ly_kernel(const __grid_cons
         }
       }
     }
+    if (warp == 0) { LPROBE(2) LPROBE_DUMP(2) }
   }
 
   if (warp == LY_RED_WARP && q.is_heads && (p.persample_out || p.bc_out) && MODE != IAF_MODE_MULTICONV) {

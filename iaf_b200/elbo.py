@@ -183,8 +183,7 @@ class CudaIAFTrain(object):
     with respect to every parameter, the masked-AR ones included (masked taps get exactly zero, ar.py:369-373)."""
 
     def __init__(self, params, hps, path="auto", fused=False):
-        """fused=True: the whole block runs as ONE autograd node (iaf_layer_fwd / iaf_layer_bwd); needs
-        IAF_LAYER_AUTOGRAD=1 (opt-in until that node has had its first GPU run)."""
+        """fused=True: the whole block runs as ONE autograd node (iaf_layer_fwd / iaf_layer_bwd)."""
         from .ops import IAFOperator
         self.ops = {}
         self.params, self.hps, self.path, self.IAFOperator, self.fused = params, hps, path, IAFOperator, fused
@@ -201,7 +200,7 @@ class CudaIAFTrain(object):
         if self.fused:
             z, _, kl_bc, kl_cost = op.layer(eps, post_mean, post_logsd, prior_mean, prior_logsd, context, want_kl=False)
             if not z.requires_grad:
-                raise RuntimeError("CudaIAFTrain(fused=True) needs IAF_LAYER_AUTOGRAD=1")
+                raise RuntimeError("CudaIAFTrain(fused=True): the fused layer node is switched off (IAF_LAYER_AUTOGRAD=0)")
             return z, kl_bc, kl_cost
         return stochastic_layer(lambda z, c: op.step(z, c, want_logdet=False)[:2], eps, post_mean, post_logsd, prior_mean,
                                 prior_logsd, context)

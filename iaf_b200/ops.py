@@ -101,11 +101,9 @@ class IAFOperator(object):
         """Identity of the packed weights: (storage, version counter) of every parameter tensor plus the operator's own
         epoch.  In-place updates through ``.data`` (``p.data.copy_``, the usual spelling in older training loops and in
         ports of the reference's ``postup``) do NOT bump ``_version``; callers that update parameters that way call
-        ``invalidate()`` (or ``set_weights`` again, which does).  While any parameter requires grad the packed copy is
-        not trusted at all and every call re-packs (two small launches)."""
+        ``invalidate()`` (or ``set_weights`` with new tensors, which does).  Calls recorded for autograd never trust the
+        packed copy: they invalidate first (two small launches per call), see ``_for_training``."""
         ls = self._layers if layers is None else layers
-        if torch.is_grad_enabled() and any(t.requires_grad for l in ls for t in l):
-            self._epoch += 1
         return (self._epoch,) + tuple((t.data_ptr(), t._version) for l in ls for t in l)
 
     def invalidate(self):
@@ -163,8 +161,18 @@ class IAFOperator(object):
             pass
 
     # ---- introspection --------------------------------------------------------------
-    def path_used(self, H, W, device):
-        return _lib.PATH_NAMES[self._lib.iaf_plan_path(self._plan(H, W, torch.device(device)))]
+    def path_used(self, H, W, device, entry=None):
+        """Kernel family this operator runs on for (H, W): "tc" or "simt".  With ``entry`` ("step" | "multiconv" |
+        "layer") the answer is for THAT entry point: an ``path="auto"`` operator may serve one entry on the SIMT kernel
+        although the plan is a tensor-core plan (e.g. ``layer`` when its scratch does not fit); ``path="tc"`` operators
+        raise NotImplementedError from such a call instead of slowing down 10-40x."""
+        plan = self._plan(H, W, torch.device(device))
+        if entry is None:
+            return _lib.PATH_NAMES[self._lib.iaf_plan_path(plan)]
+        rc = self._lib.iaf_plan_path_for_entry(plan, _lib.ENTRIES[entry])
+        if rc < 0:
+            _lib.check(rc)
+        return _lib.PATH_NAMES[rc]
 
     def launch_count(self):
         return sum(int(self._lib.iaf_plan_launch_count(e[0])) for e in self._plans.values())
@@ -193,6 +201,7 @@ class IAFOperator(object):
         """The un-fused stack: list of head outputs (ar.py:396-416 / layers.py:158-166).  Differentiable: when an
         input or a parameter requires grad the call is recorded for autograd (backward = iaf_multiconv_bwd)."""
         if self._needs_grad(z, context):
+            self.invalidate()  # training: parameters may have been stepped through .data since the last call
             flat = [t for l in self._layers for t in l]
             return list(_MulticonvFn.apply(self, z, context if self.hidden else None, *flat))
         return self._multiconv_raw(z, context)
@@ -210,6 +219,7 @@ class IAFOperator(object):
         """(z', arw_logsd [B,C,H,W], logdet [B]); logqs_new = logqs + arw_logsd.  Differentiable: when an input or a
         parameter requires grad the call is recorded for autograd (backward = iaf_step_bwd)."""
         if self._needs_grad(z, context):
+            self.invalidate()  # training: parameters may have been stepped through .data since the last call
             flat = [t for l in self._layers for t in l]
             z_out, logsd, logdet = _StepFn.apply(self, z, context if self.hidden else None, *flat)
             self._nan_guard(logdet)
@@ -279,7 +289,7 @@ class IAFOperator(object):
         B, _, H, W = z.shape
         device = torch.device("cuda", torch.cuda.current_device())
         self._host_plan = self._plan(H, W, device)
-        torch.cuda.current_stream(device).synchronize()  # weights packed on the caller's stream are visible
+        # (weights packed on the caller's stream: the library orders its private compute stream after it, one event)
         _lib.check(self._lib.iaf_step_submit_host(self._host_plan, _ptr(z), _ptr(context), _ptr(z_out), _ptr(logsd_out),
                                                   _ptr(logdet_out), B))
 
@@ -289,10 +299,12 @@ class IAFOperator(object):
 
     def layer(self, eps, post_mean, post_logsd, prior_mean, prior_logsd, context, want_kl=True):
         """Fused posterior-sample -> IAF step -> KL block (tf_train.py:56-85, models.py:273-328).
-        Returns (z', kl [B,C,H,W] or None, kl_bc [B,C], kl_cost [B]).  With IAF_LAYER_AUTOGRAD=1 (opt-in until its first
-        GPU run; the kernels are emulation-tested) the call is differentiable: backward = iaf_layer_bwd."""
-        if os.environ.get("IAF_LAYER_AUTOGRAD", "0") == "1" and self._needs_grad(eps, post_mean, post_logsd, prior_mean,
+        Returns (z', kl [B,C,H,W] or None, kl_bc [B,C], kl_cost [B]).  Differentiable: when an input or a parameter
+        requires grad the call is ONE autograd node (backward = iaf_layer_bwd; confirmed on a B200 in round 2:
+        worst relative gradient error 6.4e-4 on the whole training objective).  IAF_LAYER_AUTOGRAD=0 switches it off."""
+        if os.environ.get("IAF_LAYER_AUTOGRAD", "1") != "0" and self._needs_grad(eps, post_mean, post_logsd, prior_mean,
                                                                                    prior_logsd, context):
+            self.invalidate()  # training: parameters may have been stepped through .data since the last call
             flat = [t for l in self._layers for t in l]
             z_out, kl, kl_bc, kl_cost = _LayerFn.apply(self, eps, post_mean, post_logsd, prior_mean, prior_logsd,
                                                        context if self.hidden else None, *flat)
@@ -458,12 +470,12 @@ class _LayerFn(torch.autograd.Function):
 class _MulticonvFn(torch.autograd.Function):
     """autograd node of the un-fused operator: forward = iaf_multiconv_fwd, backward = iaf_multiconv_bwd."""
 
-    # IAF_MULTICONV_SAVED=1 (opt-in until confirmed on the GPU, tools/round2_first_call.sh): keep the hidden activations
-    # in the forward (iaf_multiconv_fwd_train) and skip the recompute in the backward (iaf_multiconv_bwd_saved), as the
-    # fused step's node already does.  Default: recompute (the path the round-1 GPU tests ran).
+    # The forward keeps the hidden activations (iaf_multiconv_fwd_train) and the backward skips the recompute
+    # (iaf_multiconv_bwd_saved), as the fused step's node does (confirmed on a B200 in round 2).
+    # IAF_MULTICONV_SAVED=0 falls back to recomputing them in the backward.
     @staticmethod
     def forward(ctx, op, z, context, *flat):
-        ctx.keep = os.environ.get("IAF_MULTICONV_SAVED", "0") == "1"
+        ctx.keep = os.environ.get("IAF_MULTICONV_SAVED", "1") != "0"
         with torch.no_grad():
             if ctx.keep:
                 outs, hidden = op._multiconv_train_raw(z, context)
@@ -493,7 +505,8 @@ class _MulticonvFn(torch.autograd.Function):
 # ------------------------------------------------------------------------------------
 # TF-style entry: tf_utils/layers.py:158-166
 # ------------------------------------------------------------------------------------
-_TF_OPS = {}
+_TF_OPS = {}       # call-site key -> IAFOperator, in least-recently-used order
+_TF_OPS_MAX = 256
 
 
 def _tf_layers(name, params, n_h, n_out):
@@ -521,11 +534,16 @@ def ar_multiconv2d(name, x, context, n_h, n_out, nl="elu", params=None, path="au
     if params is None:
         raise ValueError("params (the variable store) is required in eager mode")
     nl = _nl_name(nl)
-    key = (name, id(params), tuple(n_h), tuple(n_out), nl, path)
-    op = _TF_OPS.get(key)
+    # one operator (plans + packed weights) per distinct call site; the parameters are re-bound on every call, so two
+    # variable stores sharing a scope name stay correct (they re-pack when they alternate) and nothing is keyed on
+    # id(params), which python recycles
+    key = (name, int(x.shape[1]), tuple(n_h), tuple(n_out), nl, path)
+    op = _TF_OPS.pop(key, None)
     if op is None:
         op = IAFOperator("tf", x.shape[1], n_h, n_out, nl=nl, path=path)
-        _TF_OPS[key] = op
+        while len(_TF_OPS) >= _TF_OPS_MAX:
+            _TF_OPS.pop(next(iter(_TF_OPS)))  # least recently used
+    _TF_OPS[key] = op  # (re-)insert as most recently used
     op.set_weights(_tf_layers(name, params, n_h, n_out))
     return op.multiconv(x, context)
 

@@ -68,7 +68,11 @@ typedef struct iaf_desc {
   int path;                   /* iaf_path                                                   */
 } iaf_desc_t;
 
-typedef struct iaf_plan iaf_plan_t; /* opaque: packed weights, scratch, launch geometry */
+/* opaque: packed weights, scratch, launch geometry.  A plan is NOT re-entrant: its scratch serves one call at a time.
+ * Calls on the same stream are ordered by the stream; when consecutive calls use different streams the library makes the
+ * later stream wait for the earlier one (one event), so results stay correct -- but two streams never run the same plan
+ * concurrently.  Use one plan per concurrent stream. */
+typedef struct iaf_plan iaf_plan_t;
 
 /* Validate the description and allocate the plan (replaces the graph-construction half of
  * ar.multiconv2d, ar.py:378-394, incl. its asserts).  */
@@ -214,6 +218,12 @@ const char* iaf_strerror(int status);
 const char* iaf_last_cuda_error(void);          /* message of the last failing CUDA call (thread-local) */
 int iaf_version(void);                          /* 10000*major + 100*minor + patch                      */
 int iaf_plan_path(const iaf_plan_t* plan);      /* iaf_path actually selected (SIMT or TC)              */
+/* The path ONE entry point runs on this plan.  A plan created with IAF_PATH_AUTO serves an entry the tensor-core kernels
+ * cannot take for this shape (e.g. the fused layer's per-(sample, channel) scratch does not fit next to the resident
+ * weights) on the exact-fp32 SIMT kernel -- 10-40x slower -- and says so here; a plan created with IAF_PATH_TC never
+ * downgrades: that entry returns IAF_ERR_UNSUPPORTED, and so does this function. */
+typedef enum { IAF_ENTRY_MULTICONV = 0, IAF_ENTRY_STEP = 1, IAF_ENTRY_LAYER = 2 } iaf_entry;
+int iaf_plan_path_for_entry(const iaf_plan_t* plan, int entry);
 uint64_t iaf_plan_launch_count(const iaf_plan_t* plan); /* kernels launched through this plan so far    */
 size_t iaf_plan_algorithmic_bytes(const iaf_plan_t* plan, int B); /* SURVEY 8d bytes of one iaf_step_fwd */
 double iaf_plan_algorithmic_flops(const iaf_plan_t* plan, int B); /* 2*B*H*W*sum nnz(mask)              */

@@ -214,8 +214,6 @@ def test_tf_training_gradients_over_the_emulated_abi(monkeypatch, fused):
     for p in (p32, p64):
         for v in p.values():
             v.requires_grad_(True)
-    if fused:   # the whole stochastic-layer block as one autograd node (iaf_layer_fwd / iaf_layer_bwd), opt-in
-        monkeypatch.setenv("IAF_LAYER_AUTOGRAD", "1")
     got = elbo.forward(p32, x, n32, elbo.CudaIAFTrain(p32, hps, path="simt", fused=fused), hps)
     ref = elbo.forward(p64, x, n64, TorchIAF(p64, hps), hps)
     np.testing.assert_allclose(float(got["obj"].detach()), float(ref["obj"].detach()), rtol=2e-5)

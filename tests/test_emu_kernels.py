@@ -199,7 +199,8 @@ def test_python_autograd_glue_over_the_emulated_abi(monkeypatch):
                 [{k: v.detach() for k, v in l.items()} for l in thh])[0].square().sum().backward()
     assert _rel(z2.grad.numpy(), zt2.grad) < TOL
 
-    # un-fused operator, second head unused
+    # un-fused operator, second head unused (first with the recompute backward, IAF_MULTICONV_SAVED=0)
+    monkeypatch.setenv("IAF_MULTICONV_SAVED", "0")
     for t in [zg, cg] + [t for l in dev for t in l]:
         t.grad = None
     m, s = op.multiconv(zg, cg)
@@ -211,19 +212,17 @@ def test_python_autograd_glue_over_the_emulated_abi(monkeypatch):
     assert _rel(dev[1][0].grad.numpy(), thh[0]["V"].grad) < TOL
     assert float(dev[2][0].grad.abs().max()) == 0.0   # head 1 received no gradient
 
-    # opt-in kept-activation path of the un-fused operator gives the same gradients
-    monkeypatch.setenv("IAF_MULTICONV_SAVED", "1")
+    # the default kept-activation path of the un-fused operator gives the same gradients
+    monkeypatch.delenv("IAF_MULTICONV_SAVED")
     ref_gz, ref_gv = zg.grad.clone(), dev[1][0].grad.clone()
     for t in [zg, cg] + [t for l in dev for t in l]:
         t.grad = None
     op.multiconv(zg, cg)[0].sum().backward()
     assert torch.allclose(zg.grad, ref_gz, rtol=1e-5, atol=1e-6) and torch.allclose(dev[1][0].grad, ref_gv, rtol=1e-5, atol=1e-6)
-    monkeypatch.delenv("IAF_MULTICONV_SAVED")
 
-    # opt-in autograd node of the fused layer block (iaf_layer_fwd / iaf_layer_bwd) against the same block built from
+    # autograd node of the fused layer block (iaf_layer_fwd / iaf_layer_bwd) against the same block built from
     # torch ops around the differentiable step
     from iaf_b200.elbo import stochastic_layer
-    monkeypatch.setenv("IAF_LAYER_AUTOGRAD", "1")
     g = torch.Generator().manual_seed(4)
     mk = lambda s_=1.0: (s_ * torch.randn(z.shape, generator=g)).requires_grad_(True)
     eps_t, pm, pls, prm, prl = torch.randn(z.shape, generator=g), mk(), mk(0.3), mk(), mk(0.3)
@@ -238,7 +237,6 @@ def test_python_autograd_glue_over_the_emulated_abi(monkeypatch):
     (z2.square().sum() + torch.clamp(bc2.mean(dim=0), min=0.25).sum() + 0.5 * cost2.sum()).backward()
     for a, t in zip(got, (pm, pls, prm, prl, cg, dev[0][0], dev[2][1])):
         assert float((a - t.grad).abs().max()) <= 2e-5 * max(float(t.grad.abs().max()), 1e-6)
-    monkeypatch.delenv("IAF_LAYER_AUTOGRAD")
 
     # the reference driver's NaN guard (graphy/function.py:107-110), opt-in
     opn = ops.IAFOperator(variant, n_z, hidden, [n_z, n_z], nl="elu", path="simt", checknan="raise").set_weights(frozen)

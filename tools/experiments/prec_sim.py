@@ -74,3 +74,27 @@ for name, hidden in (("c2a", [64]), ("c2b", [160, 160])):
         ez = float((got[0]-ref[0]).abs().max() / max(ref[0].abs().max(), 1.0))
         el = float((got[1]-ref[1]).abs().max() / max(ref[1].abs().max(), 1.0))
         print("  %s weights %-7s activations %-7s rel err z' %.2e  logdet %.2e" % (name, wq, aq, ez, el))
+
+print("---- round 2: per-SAMPLE log-det error (|d logdet_n| / max(|logdet_n|, 1)), weights bf16+bf16 vs fp16+fp16 ----")
+def quant2(x, mode):
+    if mode == "fp16x2":
+        hi = x.to(torch.float16).to(x.dtype); lo = (x - hi).to(torch.float16).to(x.dtype); return hi + lo
+    return quant(x, mode)
+for name, hidden in (("c2a", [64]), ("c2b", [160, 160])):
+    B = 64 if name == "c2a" else 32
+    hid, hd = O.make_params("tf", 32, hidden, [32, 32], seed=1)
+    z, ctx = O.make_inputs(B, 32, hidden[0], 16, 16, seed=0)
+    f64 = lambda ls: OT.to_torch(O.cast_params(ls, np.float64), torch.float64)
+    th, thh = f64(hid), f64(hd)
+    zt, ct = torch.from_numpy(z).double(), torch.from_numpy(ctx).double()
+    ref = step_w(zt, ct, th, thh, "exact", "exact")
+    for wq, aq in (("bf16x2", "bf16x2"), ("fp16x2", "bf16x2"), ("fp16x2", "exact"), ("exact", "bf16x2")):
+        x = zt
+        for i, l in enumerate(th):
+            x = conv_w(quant2(x, aq), quant2(eff_w(l, False), wq), l["b"])
+            if i == 0: x = x + ct
+            x = F.elu(x)
+        m = conv_w(quant2(x, aq), quant2(eff_w(thh[0], True), wq), thh[0]["b"]); s = conv_w(quant2(x, aq), quant2(eff_w(thh[1], True), wq), thh[1]["b"])
+        ld = -(0.1*s).flatten(1).sum(1)
+        per = ((ld - ref[1]).abs() / ref[1].abs().clamp(min=1.0))
+        print("  %s weights %-7s activations %-7s  worst per-sample logdet err %.2e (abs %.2e)" % (name, wq, aq, float(per.max()), float((ld-ref[1]).abs().max())))
