@@ -445,7 +445,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
     // a single elected lane issues the MMAs and commits
     {
       mbar_wait(&bars[BAR_W], 0);
-      const int shifts[IAF_NTAPS] = {0, 1, p.Wp - 1, p.Wp, p.Wp + 1};
       for (int s = -1; s <= s_max; ++s) {
         for (int j = 0; j < nst; ++j) {
           const int k = s + 1 - 2 * j;
@@ -479,9 +478,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
           const int nks = St.cin >> 4;
           if (elect_one_sync()) {
           uint32_t acc = 0;
-#pragma unroll
+          // (rolled on purpose: unrolled over the taps this issue code was 175 tcgen05.mma instructions / ~35 KB of SASS
+          //  per kernel and missed the instruction cache on every burst; see iaf_fz.cuh)
+#pragma unroll 1
           for (int tp = 0; tp < IAF_NTAPS; ++tp) {
-            uint32_t ah = ah0 + (uint32_t)shifts[tp], al = al0 + (uint32_t)shifts[tp];
+            const uint32_t shv = tp < 2 ? (uint32_t)tp : (uint32_t)(p.Wp + tp - 3);  // slot shifts 0, 1, Wp-1, Wp, Wp+1
+            uint32_t ah = ah0 + shv, al = al0 + shv;
+#pragma unroll 1
             for (int ks = 0; ks < nks; ++ks) {
               if (merged) {
                 // hi * [hi | lo] as one N' = 2N instruction (A fetched once for both), then lo * hi into the hi half
@@ -1137,6 +1140,9 @@ struct IafTcPlan {
   // the kernel has two shared-memory layouts: [0] z gathered by the loader warps (two operand windows when they fit),
   // [1] z staged by bulk copies (one operand window + an fp32 staging buffer; 16x16 planes, step / multiconv modes)
   struct FzLay { bool ok, layer_ok; int nzw, sm_zst, sm_in1, sm_bias[2], sm_part; size_t smem; } fzl[2];
+  // TMA descriptors of recently seen z tensors (the descriptor depends on the pointer and the batch size only; encoding
+  // one is a driver call, so steady-state callers that cycle through a few buffers pay for it once per buffer)
+  struct TmSlot { const float* z; int B; unsigned char tm[128]; } tm_cache[16];
   // layer-at-a-time mode (hidden widths that do not fit the fused kernel's on-chip rings)
   bool layered;
   int ly_stage[IAF_MAX_STAGES];
@@ -1670,7 +1676,18 @@ int iaf_tc_run(IafTcPlan* pl, const IafTcArgs* a, cudaStream_t stream, int* n_la
     const char* st = getenv("IAF_FZ_STAGE");
     bool staged = pl->fzl[1].ok && a->mode != IAF_MODE_LAYER && !(st && st[0] == '0');
     // the descriptor carries the z pointer, so it is encoded per call (host side, ~1 us) and travels in the parameters
-    if (staged && ((reinterpret_cast<uintptr_t>(a->z) & 15) != 0 || !encode_z_tmap(p.tmap_z, a->z, B, d.n_z, d.H, d.W))) staged = false;
+    if (staged) {
+      IafTcPlan::TmSlot& ts = pl->tm_cache[(reinterpret_cast<uintptr_t>(a->z) >> 12) & 15];
+      if (ts.z != a->z || ts.B != B) {
+        if ((reinterpret_cast<uintptr_t>(a->z) & 15) != 0 || !encode_z_tmap(ts.tm, a->z, B, d.n_z, d.H, d.W)) {
+          staged = false;
+          ts.z = nullptr;
+        } else {
+          ts.z = a->z; ts.B = B;
+        }
+      }
+      if (staged) memcpy(p.tmap_z, ts.tm, 128);
+    }
     fz_plane256 = d.H == 16 && d.W == 16 && (staged || a->mode == IAF_MODE_LAYER);
     const IafTcPlan::FzLay& L = pl->fzl[staged ? 1 : 0];
     p.nzw = L.nzw; p.sm_zst = L.sm_zst; p.sm_part = L.sm_part;

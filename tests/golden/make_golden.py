@@ -430,8 +430,10 @@ def main():
 
     # ---- IAFLayer.down (tf_train.py:46-95) -------------------------------------------
     down = {}
-    for name, kl_min in (("kl0", 0.0), ("kl01", 0.1), ("kl5", 5.0)):
-        B, zs, hs, H, W = 4, 4, 8, 6, 6
+    down_tc = {}   # a tensor-core-eligible shape (z 32, h 64, 8x8), kept in its own file
+    for name, kl_min, dims in (("kl0", 0.0, (4, 4, 8, 6, 6)), ("kl01", 0.1, (4, 4, 8, 6, 6)), ("kl5", 5.0, (4, 4, 8, 6, 6)),
+                               ("tc_kl01", 0.1, (4, 32, 64, 8, 8)), ("tc_kl0", 0.0, (3, 32, 64, 8, 8))):
+        B, zs, hs, H, W = dims
         rng = np.random.RandomState(11)
         hps = types.SimpleNamespace(h_size=hs, z_size=zs, kl_min=kl_min, batch_size=B, k=1)
         layer = train["IAFLayer"](hps, "train", False)
@@ -474,13 +476,15 @@ def main():
         x1 = layers["conv2d"]("down_conv1", tf.nn.elu(RT(inp)), 4 * zs + 2 * hs)
         pz_mean, pz_logsd, rz_mean, rz_logsd, down_context, h_det = [np.asarray(t) for t in
                                                                      train["split"](x1, 1, [zs] * 4 + [hs] * 2)]
-        down.update({name + "_" + k: v for k, v in dict(
+        (down_tc if name.startswith("tc_") else down).update({name + "_" + k: v for k, v in dict(
             inp=inp, qz_mean=np.asarray(layer.qz_mean), qz_logsd=np.asarray(layer.qz_logsd),
             up_context=np.asarray(layer.up_context), eps=eps, pz_mean=pz_mean, pz_logsd=pz_logsd,
             rz_mean=rz_mean, rz_logsd=rz_logsd, down_context=down_context, z0=rec["z0"], context=rec["context"],
             m=rec["m"], s=rec["s"], output=np.asarray(output), kl_obj=np.asarray(kl_obj),
             kl_cost=np.asarray(kl_cost), kl_min=np.float64(kl_min)).items()})
     np.savez_compressed(os.path.join(out_dir, "iaflayer_down.npz"), **down)
+    np.savez_compressed(os.path.join(out_dir, "iaflayer_down_tc.npz"), **{k: (v.astype(np.float32) if getattr(v, "ndim", 0) else v)
+                                                                         for k, v in down_tc.items()})
 
     # ---- distributions.py (logsumexp / compute_lowerbound / repeat / logps) -----------
     rng = np.random.RandomState(3)

@@ -229,3 +229,22 @@ def test_tf_training_gradients_over_the_emulated_abi(monkeypatch, fused):
         if "ar_multiconv2d" in k and k.endswith("/V"):
             mask = O.get_conv_ar_mask(3, 3, g.shape[2], g.shape[3], "layer_out" in k)
             assert bool((g.numpy()[mask == 0] == 0).all()), k
+
+
+def test_forward_against_reference_executed_cvae1_forward():
+    """elbo.forward (the restatement used for every bits/dim parity number) against what the reference's OWN
+    `CVAE1._forward` (tf_train.py:161-219, with IAFLayer.up/down, conv2d/deconv2d/ar_multiconv2d, discretized_logistic,
+    compute_lowerbound executed from /root/reference by tests/golden/make_golden_cvae1.py) produced on the same
+    parameters, image and noise: the objective, the loss and bits/dim."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "cvae1_forward.npz"))
+    for tag in ("", "kl40_"):    # free bits idle / binding (tf_train.py:77-83)
+        hps = dict(z_size=4, h_size=8, depth=2, num_blocks=2, kl_min=float(g[tag + "kl_min"]), image_size=16)
+        params = {k: torch.from_numpy(np.asarray(v, dtype=np.float64)) for k, v in elbo.make_params(hps, seed=int(g["seed"])).items()}
+        x = torch.from_numpy(g["x"])
+        noise = {(i, j): torch.from_numpy(g["noise_%d_%d" % (i, j)].astype(np.float64)) for i in range(2) for j in range(2)}
+        out = elbo.forward(params, x, noise, OracleIAF(params, hps), hps)
+        np.testing.assert_allclose(float(out["obj"]), float(g[tag + "obj"]), rtol=1e-10)
+        np.testing.assert_allclose(float((out["kl_cost"] - out["log_pxz"]).sum()), float(g[tag + "loss"]), rtol=1e-10)
+        np.testing.assert_allclose(float(out["bits_per_dim"]), float(g[tag + "bits_per_dim"]), rtol=1e-10)
+    assert float(g["kl40_obj"]) > float(g["kl40_loss"]) and float(g["obj"]) == float(g["loss"])

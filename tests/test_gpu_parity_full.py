@@ -171,3 +171,29 @@ def test_bits_per_dim_c4_full_depth():
         ref = ET.forward(wc, xc, nc, TorchIAFTheano(wc, hps), hps)
     g, r = float(got["bits_per_dim"]), float(ref["bits_per_dim"])
     assert abs(g - r) <= 1e-4 * max(abs(r), 1.0), (g, r)
+
+
+@pytest.mark.parametrize("name", ["tc_kl01", "tc_kl0"])
+def test_tensor_core_fused_layer_against_iaflayer_down_fixture(name):
+    """iaf_layer_fwd on the TENSOR-CORE path (z 32, h 64, 8x8: hidden [64, 64] runs the layer-at-a-time tcgen05 kernels in
+    their layer mode) against tensors IAFLayer.down (tf_train.py:46-95) produced when executed from the reference's source
+    (tests/golden/make_golden.py): z', kl_cost, the per-(sample, channel) KL sums and the free-bits objective."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "iaflayer_down_tc.npz"))
+    v = lambda k: g[name + "_" + k].astype(np.float64)
+    zs, hs = 32, 64
+    hid, heads = O.make_params("tf", zs, [hs, hs], [zs, zs], seed=77)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a.astype(np.float32))).cuda()
+    op = make_op("tf", zs, [hs, hs], "elu", "tc", hid, heads)
+    assert op.path_used(8, 8, "cuda:0", entry="layer") == "tc"
+    z1, kl, kl_bc, kl_cost = op.layer(t(v("eps")), t(v("rz_mean") + v("qz_mean")), t(v("rz_logsd") + v("qz_logsd")),
+                                      t(v("pz_mean")), t(v("pz_logsd")), t(v("up_context") + v("down_context")))
+    z_ref = (v("z0") - 0.1 * v("m")) / np.exp(0.1 * v("s"))
+    assert relerr(z1, z_ref) < TOL
+    assert relerr(kl_cost, v("kl_cost")) < TOL
+    assert relerr(kl.sum(dim=(2, 3)), kl_bc.cpu().numpy().astype(np.float64)) < 1e-5
+    kl_min = float(g[name + "_kl_min"])
+    if kl_min > 0:   # tf_train.py:77-83
+        kl_obj = torch.clamp(kl_bc.mean(dim=0, keepdim=True), min=kl_min).expand(kl_bc.shape[0], -1).sum(dim=1)
+    else:
+        kl_obj = kl_cost
+    assert relerr(kl_obj, v("kl_obj")) < TOL

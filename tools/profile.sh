@@ -9,9 +9,9 @@ mkdir -p gpurun_out
 # every launch with its device time (cold-cache, serialised: compare shares, not absolutes)
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv \
   --log-file gpurun_out/launches_${WL}_${TAG}.csv \
-  python bench.py --workload ${WL} --steps 10 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/launches_${WL}_${TAG}.log 2>&1
+  python bench.py --workload ${WL} --steps 10 --warmup 3 --no-graph --no-cpu-baseline --no-also --no-e2e > gpurun_out/launches_${WL}_${TAG}.log 2>&1
 # the step kernel, once, full set (skip the warm-up launches of that kernel)
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:'iaf_(tc|simt|ly)_kernel' -s 5 -c 1 -f \
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:'iaf_(fz|tc|simt|ly)_kernel' -s 5 -c 1 -f \
   -o gpurun_out/prof_${WL}_${TAG} \
-  python bench.py --workload ${WL} --steps 10 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/prof_${WL}_${TAG}.log 2>&1
+  python bench.py --workload ${WL} --steps 10 --warmup 3 --no-graph --no-cpu-baseline --no-also --no-e2e > gpurun_out/prof_${WL}_${TAG}.log 2>&1
 ls -la gpurun_out | tail -5
