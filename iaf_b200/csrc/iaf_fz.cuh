@@ -52,9 +52,9 @@ enum {
   FB_A1_EMPTY = 17, // + b
   FB_PART = 19,     // + tile parity
   FB_PART_EMPTY = 21,
-  FB_ZST_FULL = 23, // staged variant: the bulk copies of a tile's fp32 z rows have landed
-  FB_ZST_EMPTY = 24,// ... the loader warps have read them
-  FB_COUNT = 25
+  FB_ZST_FULL = 23, // + b, staged variant: the TMA copies of a tile's fp32 z rows have landed in staging buffer b
+  FB_ZST_EMPTY = 25,// + b: the loader warps have read them
+  FB_COUNT = 27
 };
 
 // Optional wait-time probe (compile with -DIAF_FZ_PROBE; development aid): the lead lane of each role in CTA 1 accumulates
@@ -153,8 +153,10 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) iaf_fz_kernel(const __grid_cons
     tmem_alloc(&s_tmem, (uint32_t)p.tmem_cols);
     if (lane == 0) {
       mbar_init(&bars[FB_W], 1);
-      mbar_init(&bars[FB_ZST_FULL], 1);
-      mbar_init(&bars[FB_ZST_EMPTY], FZ_LD);
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(&bars[FB_ZST_FULL + b], 1);
+        mbar_init(&bars[FB_ZST_EMPTY + b], FZ_LD);
+      }
       for (int b = 0; b < 2; ++b) {
         mbar_init(&bars[FB_ZFULL + b], FZ_LD);
         mbar_init(&bars[FB_ZEMPTY + b], 1);
@@ -273,14 +275,16 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) iaf_fz_kernel(const __grid_cons
         // ---------------- M1(k-1): heads ----------------
         const int kk = k - 1, b = kk & 1;
         PROBE(7)
-        mbar_wait(&bars[FB_H_FULL + b], (uint32_t)((kk >> 1) & 1));
+        const int hb = (p.nhb == 2) ? b : 0;               // hidden-activation buffer of tile kk
+        const int huse = (p.nhb == 2) ? (kk >> 1) : kk;     // how many times it has been filled before
+        mbar_wait(&bars[FB_H_FULL + hb], (uint32_t)(huse & 1));
         PROBE(3)
         if (kk >= 2) mbar_wait(&bars[FB_A1_EMPTY + b], (uint32_t)(((kk >> 1) - 1) & 1));
         PROBE(4)
         tc_fence_after();
         if (lane == 0) TL(0, 101, kk);
         const uint32_t d = tmem_base + (uint32_t)(S1.tmem_col + b * S1.acc_cols);
-        const uint32_t a_base = smem_u32(smem + S1.sm_in + b * p.h_bytes);
+        const uint32_t a_base = smem_u32(smem + S1.sm_in + hb * p.h_bytes);
         const uint32_t a1h = umma_desc_lo(a_base, a1_plane);
         const uint32_t a1l = umma_desc_lo(a_base + (uint32_t)(S1.cin >> 3) * a1_plane, a1_plane);
         if (elect_one_sync()) {
@@ -307,7 +311,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) iaf_fz_kernel(const __grid_cons
             }
           }
           umma_commit(&bars[FB_A1_FULL + b]);
-          umma_commit(&bars[FB_H_EMPTY + b]);
+          umma_commit(&bars[FB_H_EMPTY + hb]);
           TL(0, 201, kk);
         }
         __syncwarp();
@@ -404,8 +408,10 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) iaf_fz_kernel(const __grid_cons
         // into registers and hand the staging buffer back BEFORE waiting for the operand window, so that the copies of
         // tile k+1 are in flight while the MMAs of tile k-1 still own the window
         const ZstGeo g = zst_geometry(p, (t0 + k) * TO);
-        mbar_wait(&bars[FB_ZST_FULL], (uint32_t)(k & 1));
-        const float* stg = reinterpret_cast<const float*>(smem + p.sm_zst);
+        const int sb = (p.nzs == 2) ? (k & 1) : 0;
+        const int suse = (p.nzs == 2) ? (k >> 1) : k;
+        mbar_wait(&bars[FB_ZST_FULL + sb], (uint32_t)(suse & 1));
+        const float* stg = reinterpret_cast<const float*>(smem + p.sm_zst + sb * p.zst_bytes);
 #pragma unroll
         for (int it = 0; it < FZ_ZB; ++it) {
           if (z_dst[it] >= 0) {
@@ -432,7 +438,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) iaf_fz_kernel(const __grid_cons
 #pragma unroll
           for (int e = 0; e < 8; ++e) dep += v[it][e];
         __syncwarp();
-        if (lane == 0 || dep == 1.0e38f) mbar_arrive(&bars[FB_ZST_EMPTY]);
+        if (lane == 0 || dep == 1.0e38f) mbar_arrive(&bars[FB_ZST_EMPTY + sb]);
       }
       PROBE(6)
       if (!tables) {  // the bias tables travel with the weights
@@ -533,13 +539,15 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) iaf_fz_kernel(const __grid_cons
         tn_cur = t_n; tr_cur = t_r;
         advance_nr(p, t_n, t_r, TO);
         const uint32_t t_acc = t_lane + (uint32_t)(S0.tmem_col + b * S0.acc_cols);
-        uint8_t* obase = smem + S1.sm_in + b * p.h_bytes + sl * 16;
+        const int hb = (p.nhb == 2) ? b : 0;
+        const int huse = (p.nhb == 2) ? (k >> 1) : k;
+        uint8_t* obase = smem + S1.sm_in + hb * p.h_bytes + sl * 16;
         if (warp == 0 && lane == 0) TL(1, 9, k);
         PROBE(7)
         mbar_wait(&bars[FB_A0_FULL + b], (uint32_t)((k >> 1) & 1));
         tc_fence_after();
         PROBE(0)
-        if (k >= 2) mbar_wait(&bars[FB_H_EMPTY + b], (uint32_t)(((k >> 1) - 1) & 1));  // M1(k-2) has read h buffer b
+        if (huse >= 1) mbar_wait(&bars[FB_H_EMPTY + hb], (uint32_t)((huse - 1) & 1));  // the M1 that read the buffer last
         PROBE(1)
         if (warp == 0 && lane == 0) TL(1, 10, k);
         for (int g = (p.dbg & 4) ? ngroups0 : cg; g < ngroups0; g += FZ_CGS) {
@@ -595,7 +603,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) iaf_fz_kernel(const __grid_cons
         __syncwarp();
         if (lane == 0) {
           mbar_arrive(&bars[FB_A0_EMPTY + b]);
-          mbar_arrive(&bars[FB_H_FULL + b]);
+          mbar_arrive(&bars[FB_H_FULL + hb]);
         }
         if (warp == 0 && lane == 0) TL(1, 20, k);
         PROBE(2)
@@ -753,15 +761,17 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) iaf_fz_kernel(const __grid_cons
     // (Per-(sample, channel) 1-D bulk copies were measured first: 64 copies of <= 640 B per tile cost ~3 K cycles of TMA
     //  issue per tile and made this variant slower than the gathered one.)
     // =====================================================================================
-    uint8_t* stg = smem + p.sm_zst;
     const uint32_t row_bytes = (uint32_t)(p.C * p.W * 4);
     // (L2 prefetch of the rows of the tiles further ahead -- cp.async.bulk.prefetch.tensor for z and for the context --
     //  was measured: 26.8 us against 25.0 us without; the extra descriptor-based requests delay the copies themselves.)
     for (int k = 0; k < nt; ++k) {
       const ZstGeo g = zst_geometry(p, (t0 + k) * TO);
-      if (k >= 1) mbar_wait(&bars[FB_ZST_EMPTY], (uint32_t)((k - 1) & 1));
+      const int sb = (p.nzs == 2) ? (k & 1) : 0;
+      const int suse = (p.nzs == 2) ? (k >> 1) : k;
+      uint8_t* stg = smem + p.sm_zst + sb * p.zst_bytes;
+      if (suse >= 1) mbar_wait(&bars[FB_ZST_EMPTY + sb], (uint32_t)((suse - 1) & 1));
       const int nrows = g.rows0 + g.rows1;
-      if (lane == 0) mbar_expect_tx(&bars[FB_ZST_FULL], (p.dbg & 1) ? 0u : (uint32_t)nrows * row_bytes);
+      if (lane == 0) mbar_expect_tx(&bars[FB_ZST_FULL + sb], (p.dbg & 1) ? 0u : (uint32_t)nrows * row_bytes);
       __syncwarp();
       if (!(p.dbg & 1) && lane < nrows) {
         // lane r fetches staged row r: box (x 0..W-1, one image row, every channel, one sample) = C * W floats.
@@ -770,7 +780,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) iaf_fz_kernel(const __grid_cons
         const int m1 = p.flip ? p.H - g.rows1 : 0;
         const bool second = lane >= g.rows0;
         const int row = second ? m1 + (lane - g.rows0) : m0 + lane;
-        tma_load_4d(stg + (size_t)lane * row_bytes, p.tmap_z, 0, row, 0, second ? g.n1 : g.n0, &bars[FB_ZST_FULL]);
+        tma_load_4d(stg + (size_t)lane * row_bytes, p.tmap_z, 0, row, 0, second ? g.n1 : g.n0, &bars[FB_ZST_FULL + sb]);
       }
       __syncwarp();
     }

@@ -120,6 +120,9 @@ struct IafTcParams {
   int h_bytes;   // bytes of one hidden-activation operand buffer (hi + lo plane sets of 128 slots)
   int z_bytes;   // bytes of one z operand window (hi + lo plane sets of WIN slots, rounded up to 128)
   int nzw;       // z operand windows: 2 (loaders a full tile ahead) or 1
+  int nhb;       // hidden-activation operand buffers: 2, or 1 (staged variant: the space goes to a second staging buffer)
+  int nzs;       // fp32 z staging buffers (staged variant): 2 = the TMA copies run two tiles ahead of the loader warps
+  int zst_bytes; // bytes of one staging buffer
   int sm_zst;    // byte offset of the fp32 z staging buffer the bulk copies land in (staged variant, 16x16 planes)
   int dbg;       // IAF_FZ_DBG (development, timing only, results WRONG when set): 1 loaders issue no global loads,
                  // 2 loaders also skip their stores, 4 E0 does nothing but the hand-off, 8 E1 likewise, 16 no MMAs, 32 no weight load
@@ -1139,7 +1142,7 @@ struct IafTcPlan {
   int TO, h_bytes, z_bytes;
   // the kernel has two shared-memory layouts: [0] z gathered by the loader warps (two operand windows when they fit),
   // [1] z staged by bulk copies (one operand window + an fp32 staging buffer; 16x16 planes, step / multiconv modes)
-  struct FzLay { bool ok, layer_ok; int nzw, sm_zst, sm_in1, sm_bias[2], sm_part; size_t smem; } fzl[2];
+  struct FzLay { bool ok, layer_ok; int nzw, nhb, nzs, zst_bytes, sm_zst, sm_in1, sm_bias[2], sm_part; size_t smem; } fzl[2];
   // TMA descriptors of recently seen z tensors (the descriptor depends on the pointer and the batch size only; encoding
   // one is a driver call, so steady-state callers that cycle through a few buffers pay for it once per buffer)
   struct TmSlot { const float* z; int B; unsigned char tm[128]; } tm_cache[16];
@@ -1294,16 +1297,24 @@ static bool fz_layout(const iaf_desc_t* d, IafTcPlan* pl) {
     L.ok = false;
     // staged: 16x16 planes only (the kernel's compile-time-plane instantiation is the staged one)
     if (v == 1 && !(d->H == 16 && d->W == 16 && d->n_z <= 32 && tmap_encoder())) continue;
-    for (int nzw = (v == 1 ? 1 : 2); nzw >= 1 && !L.ok; --nzw) {
+    // gathered: two z windows when they fit (else one), two h buffers.  Staged: one z window, one staging buffer, two h
+    // buffers.  (IAF_FZ_TWO_STAGE=1 selects two staging buffers paid for with ONE h buffer -- measured on the B200: 26.2 us
+    // against 25.2 us; the loader warps wait just as long for the copies, so a tile's copy TIME, not how early it is
+    // issued, is what they wait for: ten boxes of 32 x 64-byte segments each, see profiles/r2_fz_probe_staging.log.)
+    const int rows = (q->WIN + Wp - 2) / Wp + 1;  // stream rows a window can touch
+    const int zst_bytes = tc_round_up(d->n_z * rows * d->W * 4, 128);
+    const char* e2 = getenv("IAF_FZ_TWO_STAGE");
+    const bool two_stage = v == 1 && e2 && e2[0] == '1';
+    for (int t = 0; t < 2 && !L.ok; ++t) {
+      const int nzw = (v == 1) ? 1 : 2 - t;
+      const int nzs = (v == 1) ? (two_stage && t == 0 ? 2 : 1) : 0;
+      const int nhb = (two_stage && t == 0) ? 1 : 2;
       int o = zoff + nzw * q->z_bytes;
-      L.nzw = nzw;
+      L.nzw = nzw; L.nhb = nhb; L.nzs = nzs; L.zst_bytes = zst_bytes;
       L.sm_zst = o;
-      if (v == 1) {
-        const int rows = (q->WIN + Wp - 2) / Wp + 1;  // stream rows a window can touch
-        o += tc_round_up(d->n_z * rows * d->W * 4, 128);
-      }
+      o += nzs * zst_bytes;
       L.sm_in1 = o;
-      o += 2 * q->h_bytes;
+      o += nhb * q->h_bytes;
       o += tc_round_up(MIR * 16, 128);  // a shifted 128-row window of the last plane reads MIR rows past the buffer
       for (int j = 0; j < 2; ++j) { L.sm_bias[j] = o; o += 5 * q->N[j] * 4; }
       o = tc_round_up(o, 16);
@@ -1690,7 +1701,8 @@ int iaf_tc_run(IafTcPlan* pl, const IafTcArgs* a, cudaStream_t stream, int* n_la
     }
     fz_plane256 = d.H == 16 && d.W == 16 && (staged || a->mode == IAF_MODE_LAYER);
     const IafTcPlan::FzLay& L = pl->fzl[staged ? 1 : 0];
-    p.nzw = L.nzw; p.sm_zst = L.sm_zst; p.sm_part = L.sm_part;
+    p.nzw = L.nzw; p.nhb = L.nhb; p.nzs = L.nzs; p.zst_bytes = L.zst_bytes; p.sm_zst = L.sm_zst; p.sm_part = L.sm_part;
+
     p.st[1].sm_in = L.sm_in1;
     p.st[0].sm_bias = L.sm_bias[0]; p.st[1].sm_bias = L.sm_bias[1];
     fz_smem = L.smem;
