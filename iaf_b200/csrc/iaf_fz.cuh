@@ -40,7 +40,7 @@
 #define FZ_CGS (FZ_EPI / 4) // epilogue warps sharing one lane quadrant
 
 enum {
-  FB_W = 0,         // weights + bias tables have landed (bulk copies)
+  FB_W = 0,         // bias tables + stage-0 weights have landed (bulk copies); the stage-1 weights: FB_W1
   FB_ZFULL = 1,     // + b: z window b written
   FB_ZEMPTY = 3,    // + b: M0 committed (z window b read)
   FB_A0_INIT = 5,   // + b: context + bias written into accumulator b of stage 0
@@ -54,7 +54,8 @@ enum {
   FB_PART_EMPTY = 21,
   FB_ZST_FULL = 23, // + b, staged variant: the TMA copies of a tile's fp32 z rows have landed in staging buffer b
   FB_ZST_EMPTY = 25,// + b: the loader warps have read them
-  FB_COUNT = 27
+  FB_W1 = 27,       // stage-1 (heads) weights have landed: only M1(0) waits for them, M0(0) starts 80 KB earlier
+  FB_COUNT = 28
 };
 
 // Optional wait-time probe (compile with -DIAF_FZ_PROBE; development aid): the lead lane of each role in CTA 1 accumulates
@@ -153,6 +154,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) iaf_fz_kernel(const __grid_cons
     tmem_alloc(&s_tmem, (uint32_t)p.tmem_cols);
     if (lane == 0) {
       mbar_init(&bars[FB_W], 1);
+      mbar_init(&bars[FB_W1], 1);
       for (int b = 0; b < 2; ++b) {
         mbar_init(&bars[FB_ZST_FULL + b], 1);
         mbar_init(&bars[FB_ZST_EMPTY + b], FZ_LD);
@@ -173,15 +175,16 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) iaf_fz_kernel(const __grid_cons
       fence_barrier_init();
       asm volatile("griddepcontrol.wait;" ::: "memory");
       const uint32_t tab0 = 5u * (uint32_t)S0.N * 4u, tab1 = 5u * (uint32_t)S1.N * 4u;
-      const uint32_t total = (p.dbg & 32) ? tab0 + tab1 : 2u * (uint32_t)S0.w_bytes + 2u * (uint32_t)S1.w_bytes + tab0 + tab1;
-      mbar_expect_tx(&bars[FB_W], total);
+      const bool now = (p.dbg & 32) != 0;  // timing only: no weight load
+      mbar_expect_tx(&bars[FB_W], tab0 + tab1 + (now ? 0u : 2u * (uint32_t)S0.w_bytes));
+      mbar_expect_tx(&bars[FB_W1], now ? 0u : 2u * (uint32_t)S1.w_bytes);
       // bias tables [5][N] (row 0 bias, rows 1..4 the Theano pad-channel weights; zero for the TF variant)
       bulk_g2s(smem + S0.sm_bias, S0.bias, tab0, &bars[FB_W]);
       bulk_g2s(smem + S1.sm_bias, S1.bias, tab1, &bars[FB_W]);
-      for (int j = 0; j < ((p.dbg & 32) ? 0 : 2); ++j) {
+      for (int j = 0; j < (now ? 0 : 2); ++j) {
         for (int off = 0; off < 2 * p.st[j].w_bytes; off += 32768) {
           const uint32_t n = (uint32_t)min(32768, 2 * p.st[j].w_bytes - off);
-          bulk_g2s(smem + p.st[j].sm_whi + off, reinterpret_cast<const uint8_t*>(p.st[j].whi) + off, n, &bars[FB_W]);
+          bulk_g2s(smem + p.st[j].sm_whi + off, reinterpret_cast<const uint8_t*>(p.st[j].whi) + off, n, &bars[j ? FB_W1 : FB_W]);
         }
       }
     }
@@ -194,7 +197,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) iaf_fz_kernel(const __grid_cons
   const uint32_t tmem_base = s_tmem;
 
   if (p.dbg & 128) {  // timing only: prologue + teardown, no roles
-    if (warp == FZ_W_MMA) mbar_wait(&bars[FB_W], 0);
+    if (warp == FZ_W_MMA) { mbar_wait(&bars[FB_W], 0); mbar_wait(&bars[FB_W1], 0); }
   } else
   if (warp == FZ_W_MMA) {
     // =====================================================================================
@@ -275,6 +278,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) iaf_fz_kernel(const __grid_cons
         // ---------------- M1(k-1): heads ----------------
         const int kk = k - 1, b = kk & 1;
         PROBE(7)
+        if (kk == 0) mbar_wait(&bars[FB_W1], 0);
         const int hb = (p.nhb == 2) ? b : 0;               // hidden-activation buffer of tile kk
         const int huse = (p.nhb == 2) ? (kk >> 1) : kk;     // how many times it has been filled before
         mbar_wait(&bars[FB_H_FULL + hb], (uint32_t)(huse & 1));
@@ -404,7 +408,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) iaf_fz_kernel(const __grid_cons
       if (lw == 0 && lane == 0) TL(3, 41, k);
       PROBE(0)
       if (ZST) {
-        // the tile's fp32 rows were staged by the TMA warp as [staged row][channel][x]: read this thread's items
+        // the tile's fp32 rows were staged by the TMA warp as [sample][channel][row][x]: read this thread's items
         // into registers and hand the staging buffer back BEFORE waiting for the operand window, so that the copies of
         // tile k+1 are in flight while the MMAs of tile k-1 still own the window
         const ZstGeo g = zst_geometry(p, (t0 + k) * TO);
@@ -425,9 +429,10 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) iaf_fz_kernel(const __grid_cons
               const int ylo = second ? 0 : g.y0;
               const int rel = p.flip ? (ylo + rows - 1 - zi.y) : (zi.y - ylo);
               const int xx = p.flip ? (p.W - 1 - zi.x) : zi.x;
-              const float* sp = stg + ((second ? g.rows0 : 0) + rel) * (p.C * p.W) + (z_cho[it] / HW) * p.W + xx;
+              const int cstride = rows * p.W;
+              const float* sp = stg + (second ? p.C * g.rows0 * p.W : 0) + (z_cho[it] / HW) * cstride + rel * p.W + xx;
 #pragma unroll
-              for (int e = 0; e < 8; ++e) v[it][e] = sp[e * p.W];
+              for (int e = 0; e < 8; ++e) v[it][e] = sp[e * cstride];
             }
           }
         }
@@ -756,10 +761,12 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) iaf_fz_kernel(const __grid_cons
   } else if (ZST && warp == FZ_W_TMA) {
     // =====================================================================================
     // TMA producer (staged variant): the fp32 rows of z a tile's window touches -> staging buffer, as tiled tensor
-    // copies (cp.async.bulk.tensor.4d over z viewed as (x, y, channel, sample)): one box = one image row of every
-    // channel, <= 10 boxes per tile, issued by the warp's lanes in parallel and completing on one mbarrier (expect_tx).
-    // (Per-(sample, channel) 1-D bulk copies were measured first: 64 copies of <= 640 B per tile cost ~3 K cycles of TMA
-    //  issue per tile and made this variant slower than the gathered one.)
+    // copies (cp.async.bulk.tensor.4d over z viewed as (x, y, channel, sample)): ONE box per sample = its rows of every
+    // channel (the box height is a property of the descriptor, so the parameters carry one descriptor per row count),
+    // <= 2 boxes per tile, completing on one mbarrier (expect_tx).
+    // (Measured before this: per-(sample, channel) 1-D bulk copies, 64 copies of <= 640 B per tile: ~3 K cycles of TMA
+    //  issue per tile, slower than gathering; one box per image ROW, 10 boxes of 32 x 64-byte segments: faster than
+    //  gathering, the loader warps still waited ~2.5 K cycles per tile for them.)
     // =====================================================================================
     const uint32_t row_bytes = (uint32_t)(p.C * p.W * 4);
     // (L2 prefetch of the rows of the tiles further ahead -- cp.async.bulk.prefetch.tensor for z and for the context --
@@ -773,14 +780,16 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) iaf_fz_kernel(const __grid_cons
       const int nrows = g.rows0 + g.rows1;
       if (lane == 0) mbar_expect_tx(&bars[FB_ZST_FULL + sb], (p.dbg & 1) ? 0u : (uint32_t)nrows * row_bytes);
       __syncwarp();
-      if (!(p.dbg & 1) && lane < nrows) {
-        // lane r fetches staged row r: box (x 0..W-1, one image row, every channel, one sample) = C * W floats.
-        // First staged memory row of each sample (Theano orientation: the stream is the point-reflected image)
+      if (!(p.dbg & 1) && lane < 2) {
+        // lane 0 fetches sample n0's rows, lane 1 sample n1's: ONE box each (x 0..W-1, `rows` image rows, every channel),
+        // taken from the descriptor whose box has exactly that many rows.  First staged memory row of each sample (Theano
+        // orientation: the stream is the point-reflected image):
         const int m0 = p.flip ? p.H - g.y0 - g.rows0 : g.y0;
         const int m1 = p.flip ? p.H - g.rows1 : 0;
-        const bool second = lane >= g.rows0;
-        const int row = second ? m1 + (lane - g.rows0) : m0 + lane;
-        tma_load_4d(stg + (size_t)lane * row_bytes, p.tmap_z, 0, row, 0, second ? g.n1 : g.n0, &bars[FB_ZST_FULL + sb]);
+        const int rws = lane ? g.rows1 : g.rows0;
+        if (rws > 0)
+          tma_load_4d(stg + (lane ? (size_t)g.rows0 * row_bytes : 0), p.tmap_z[rws - 1], 0, lane ? m1 : m0, 0, lane ? g.n1 : g.n0,
+                      &bars[FB_ZST_FULL + sb]);
       }
       __syncwarp();
     }

@@ -90,10 +90,11 @@ struct IafTcStage {
   int acc_cols;              // N or 2N
 };
 
+#define IAF_FZ_MAXROWS 10  // image rows a 16x16 tile window can touch ((WIN + Wp - 2) / Wp + 1)
 struct IafTcParams {
   // iaf_fz_kernel, staged variant: TMA descriptor of z viewed as a 4-D tensor (x, y, channel, sample), box = one image
   // row of every channel; 64-byte aligned as the hardware requires of a descriptor passed in kernel-parameter space
-  alignas(64) unsigned char tmap_z[128];
+  alignas(64) unsigned char tmap_z[IAF_FZ_MAXROWS][128];  // [r - 1]: box = r image rows of every channel of one sample
   const float* z; const float* ctx;
   const float* post_mean; const float* post_logsd; const float* prior_mean; const float* prior_logsd;
   float* z_out; float* elem; float* bc_out; float* persample_out;
@@ -1145,7 +1146,7 @@ struct IafTcPlan {
   struct FzLay { bool ok, layer_ok; int nzw, nhb, nzs, zst_bytes, sm_zst, sm_in1, sm_bias[2], sm_part; size_t smem; } fzl[2];
   // TMA descriptors of recently seen z tensors (the descriptor depends on the pointer and the batch size only; encoding
   // one is a driver call, so steady-state callers that cycle through a few buffers pay for it once per buffer)
-  struct TmSlot { const float* z; int B; unsigned char tm[128]; } tm_cache[16];
+  struct TmSlot { const float* z; int B; unsigned char tm[IAF_FZ_MAXROWS][128]; } tm_cache[16];
   // layer-at-a-time mode (hidden widths that do not fit the fused kernel's on-chip rings)
   bool layered;
   int ly_stage[IAF_MAX_STAGES];
@@ -1217,14 +1218,15 @@ static TmapEncodeFn tmap_encoder() {
   }
   return fn;
 }
-// z [B][C][H][W] fp32 as (x, y, c, n); box = (W, 1, C, 1): one image row of every channel of one sample (C * W * 4 bytes)
-static bool encode_z_tmap(unsigned char* out128, const float* z, int B, int C, int H, int W) {
+// z [B][C][H][W] fp32 as (x, y, c, n); box = (W, rows, C, 1): `rows` image rows of every channel of one sample, which
+// land in shared memory as [channel][row][x] (per channel rows * W * 4 contiguous bytes on both sides)
+static bool encode_z_tmap(unsigned char* out128, const float* z, int B, int C, int H, int W, int rows) {
   TmapEncodeFn enc = tmap_encoder();
   if (!enc) return false;
   CUtensorMap tm;
   const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
   const cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)C * H * W * 4};
-  const cuuint32_t box[4] = {(cuuint32_t)W, 1u, (cuuint32_t)C, 1u};
+  const cuuint32_t box[4] = {(cuuint32_t)W, (cuuint32_t)rows, (cuuint32_t)C, 1u};
   const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
   if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(z), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
@@ -1302,6 +1304,7 @@ static bool fz_layout(const iaf_desc_t* d, IafTcPlan* pl) {
     // against 25.2 us; the loader warps wait just as long for the copies, so a tile's copy TIME, not how early it is
     // issued, is what they wait for: ten boxes of 32 x 64-byte segments each, see profiles/r2_fz_probe_staging.log.)
     const int rows = (q->WIN + Wp - 2) / Wp + 1;  // stream rows a window can touch
+    if (v == 1 && rows > IAF_FZ_MAXROWS) continue;
     const int zst_bytes = tc_round_up(d->n_z * rows * d->W * 4, 128);
     const char* e2 = getenv("IAF_FZ_TWO_STAGE");
     const bool two_stage = v == 1 && e2 && e2[0] == '1';
@@ -1690,14 +1693,16 @@ int iaf_tc_run(IafTcPlan* pl, const IafTcArgs* a, cudaStream_t stream, int* n_la
     if (staged) {
       IafTcPlan::TmSlot& ts = pl->tm_cache[(reinterpret_cast<uintptr_t>(a->z) >> 12) & 15];
       if (ts.z != a->z || ts.B != B) {
-        if ((reinterpret_cast<uintptr_t>(a->z) & 15) != 0 || !encode_z_tmap(ts.tm, a->z, B, d.n_z, d.H, d.W)) {
+        bool ok = (reinterpret_cast<uintptr_t>(a->z) & 15) == 0;
+        for (int r = 1; r <= IAF_FZ_MAXROWS && ok; ++r) ok = encode_z_tmap(ts.tm[r - 1], a->z, B, d.n_z, d.H, d.W, r);
+        if (!ok) {
           staged = false;
           ts.z = nullptr;
         } else {
           ts.z = a->z; ts.B = B;
         }
       }
-      if (staged) memcpy(p.tmap_z, ts.tm, 128);
+      if (staged) memcpy(p.tmap_z, ts.tm, sizeof(ts.tm));
     }
     fz_plane256 = d.H == 16 && d.W == 16 && (staged || a->mode == IAF_MODE_LAYER);
     const IafTcPlan::FzLay& L = pl->fzl[staged ? 1 : 0];
