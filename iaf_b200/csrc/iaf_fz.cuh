@@ -832,15 +832,31 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) iaf_fz_kernel(const __grid_cons
         const int i = lane + 32 * j;
         if (i < ns * cred) p.tilepart[((size_t)u * p.MAXS) * cred + i] = tot[j];
       }
-      __threadfence();  // every lane publishes its own partials before any lane touches a counter
-      __syncwarp();
+      // Publish, count, and (last tile of a sample) sum.  Step / multiconv-free modes: lane i stores sample i's partial AND
+      // bumps sample i's counter, so one acq_rel atomic orders both directions and the two device-wide fences -- each a
+      // round trip of the kernel's tail -- are not needed.  Layer mode: a sample's partials come from 32 lanes: fences.
+#ifdef IAF_FZ_FENCE_TAIL
+      constexpr bool FENCE = true;   // A/B switch: the round-2 mid-state tail (fence, atomic, fence)
+#else
+      constexpr bool FENCE = LAY;
+#endif
+      if (FENCE) {
+        __threadfence();
+        __syncwarp();
+      }
       for (int i = lane; i < ns; i += 32) {
         const int n = n_first + i;
         const int a = n * p.SPS, bb = a + p.SPS - 1;
         const int ta = a / TO, tbk = bb / TO;
         const unsigned expected = (unsigned)(tbk - ta + 1);
-        if (atomicAdd(p.counter + n, 1u) == expected - 1u) {
-          __threadfence();
+        unsigned prev;
+        if (FENCE) {
+          prev = atomicAdd(p.counter + n, 1u);
+        } else {
+          asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(p.counter + n) : "memory");
+        }
+        if (prev == expected - 1u) {
+          if (FENCE) __threadfence();
           p.counter[n] = 0u;  // ready for the next launch
           float cost = 0.f;
           for (int c = 0; c < cred; ++c) {
