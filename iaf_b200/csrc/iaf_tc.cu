@@ -191,6 +191,24 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// The same with the A-operand collector: `fill` keeps the A tile this instruction fetched, `lastuse` takes A from the
+// collector instead of shared memory (the caller names the same descriptor) and releases it.  SASS: UTCHMMA .A_KEEP / .A_REUSE.
+__device__ __forceinline__ void umma_f16_afill(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_alast(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -1731,6 +1749,9 @@ int iaf_tc_run(IafTcPlan* pl, const IafTcArgs* a, cudaStream_t stream, int* n_la
       q.S_pad = pl->img_S_pad;
       q.in_mode = j ? 1 : 0;
       q.stage_id = j;
+      // A-operand collector for the (A_hi x B_lo, A_hi x B_hi) pair of every tap: measured C2b 117.4 -> 115.2 us, C3 36.9 -> 36.3 us
+      // (profiles/r2_mma_collector.log; the "liar" test there shows the second MMA really takes A from the collector).
+      { const char* ce = getenv("IAF_LY_COLLECTOR"); q.collector = ce ? atoi(ce) : 1; }
       q.first = j == 0;
       q.is_heads = j == pl->n_stages - 1;
       q.NB = pl->ly_NB[j];

@@ -88,6 +88,7 @@ struct IafLyParams {
   int n_bchunks;               // weight chunks per tile
   int tl_enable;               // timeline builds only: this launch flushes its events
   int cs;                      // cluster size (1, 2 or 4): CTAs sharing the weight stream by TMA multicast
+  int collector;               // 1: the hi*lo / hi*hi pair of a tap shares ONE shared-memory fetch of A_hi (A collector)
   int stage_id;                // which conv stage of the stack this launch is (probe / timeline builds)
 };
 
@@ -255,12 +256,25 @@ __global__ void __launch_bounds__(LY_THREADS, 1) iaf_ly_kernel(const __grid_cons
           umma_f16(d_tmem, mk_desc(al0 + (SH)), mk_desc(bh0 + (T) * b_tstep), idesc, (ACC)); \
           umma_f16(d_tmem, mk_desc(ah0 + (SH)), mk_desc(bl0 + (T) * b_tstep), idesc, 1u);    \
           umma_f16(d_tmem, mk_desc(ah0 + (SH)), mk_desc(bh0 + (T) * b_tstep), idesc, 1u);
-          LY_TAP(0u, 0u, acc0)
-          LY_TAP(1u, sh1, 1u)
-          LY_TAP(2u, sh2, 1u)
-          LY_TAP(3u, sh3, 1u)
-          LY_TAP(4u, sh4, 1u)
+#define LY_TAP_C(T, SH, ACC)                                                                       \
+          umma_f16(d_tmem, mk_desc(al0 + (SH)), mk_desc(bh0 + (T) * b_tstep), idesc, (ACC));       \
+          umma_f16_afill(d_tmem, mk_desc(ah0 + (SH)), mk_desc(bl0 + (T) * b_tstep), idesc, 1u);    \
+          umma_f16_alast(d_tmem, mk_desc(ah0 + (SH)), mk_desc(bh0 + (T) * b_tstep), idesc, 1u);
+          if (q.collector) {
+            LY_TAP_C(0u, 0u, acc0)
+            LY_TAP_C(1u, sh1, 1u)
+            LY_TAP_C(2u, sh2, 1u)
+            LY_TAP_C(3u, sh3, 1u)
+            LY_TAP_C(4u, sh4, 1u)
+          } else {
+            LY_TAP(0u, 0u, acc0)
+            LY_TAP(1u, sh1, 1u)
+            LY_TAP(2u, sh2, 1u)
+            LY_TAP(3u, sh3, 1u)
+            LY_TAP(4u, sh4, 1u)
+          }
 #undef LY_TAP
+#undef LY_TAP_C
           if (!res) {
             if (cs == 1) umma_commit(&bars[LB_BEMPTY + stg]);
             else umma_commit_mcast(&bars[LB_BEMPTY + stg], cmask);

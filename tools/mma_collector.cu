@@ -61,7 +61,7 @@ __device__ __forceinline__ uint32_t elect_one() {
 
 // operand images (no swizzle, K-major): [K chunk of 8][row][8 halves]; rows = 160 for A (128 + room for shifts), N for B
 constexpr int A_ROWS = 160;
-constexpr int KS_MAX = 10;  // K-steps (of 16) resident
+constexpr int KS_MAX = 8;   // K-steps (of 16) resident (N = 160: 4 * 8 * (160 + 160) * 16 B = 164 KB)
 __host__ __device__ inline int a_val_hi(int r, int k) { return (r * 3 + k) % 7 - 3; }
 __host__ __device__ inline int a_val_lo(int r, int k) { return (r + 2 * k) % 5 - 2; }
 __host__ __device__ inline int b_val_hi(int n, int k) { return (n + k) % 9 - 4; }
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(128, 1) k_col(Cfg c, long long* cyc_out, float
 static size_t smem_for(int N) { return (size_t)4 * KS_MAX * A_ROWS * 16 + (size_t)4 * KS_MAX * N * 16 + 1024; }
 
 int main() {
-  cudaFuncSetAttribute(k_col, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_col, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);  // every case below fits (checked by the launch error)
   long long* dcyc;
   cudaMalloc(&dcyc, 16);
   float* dD;
@@ -188,7 +188,8 @@ int main() {
       Cfg c{N, pat, 1, 1, 0};
       cudaMemset(dD, 0, 128 * 256 * 4);
       k_col<<<1, 128, smem_for(N)>>>(c, dcyc, dD);
-      cudaError_t e = cudaDeviceSynchronize();
+      cudaError_t e = cudaGetLastError();
+      if (e == cudaSuccess) e = cudaDeviceSynchronize();
       std::vector<float> hD((size_t)128 * N);
       cudaMemcpy(hD.data(), dD, hD.size() * 4, cudaMemcpyDeviceToHost);
       int bad_true = 0, bad_refetch = 0;
@@ -213,7 +214,8 @@ int main() {
       for (int pat : {0, 1, 2, 4}) {
         Cfg c{N, pat, 10, 8, shift};
         k_col<<<148, 128, smem_for(N)>>>(c, dcyc, nullptr);
-        cudaError_t e = cudaDeviceSynchronize();
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
         long long cyc = 0;
         cudaMemcpy(&cyc, dcyc, 8, cudaMemcpyDeviceToHost);
         printf("time N=%3d shift=%d pattern %d (%-32s): %7.1f cycles per MMA (bursts of 30 incl. commit+wait) %s\n", N, shift, pat, pname[pat],
