@@ -9,8 +9,8 @@ n_z=32, 16x16.  Metric: latent elements/s = 256*n_z*H*W / t_step, wh
 
 * value      : inputs resident in HBM.  The K steps are grouped into ELBO evaluations of E steps
                (E = the number of IAF steps per ELBO of the model the workload comes from); each group
-               is one CUDA-graph replay followed by the ELBO scalar (sum of the group's log-dets) and,
-               at N > 1, ONE all-reduce of that scalar (tf_train.py:142), issued on a side stream so it
+               is one CUDA-graph replay (the E step launches, then the ELBO scalar = the sum of the
+               group's log-dets, captured in the same graph) and, at N > 1, ONE all-reduce of that scalar (tf_train.py:142), issued on a side stream so it
                overlaps the next group's kernels.  CUDA events around the whole region, max over ranks.
                The steps rotate through NSETS input/output sets whose footprint exceeds L2.
 * roofline   : the step kernel(s) alone: one CUDA graph of K back-to-back launches, CUDA events;
@@ -367,8 +367,9 @@ class DeviceBench(object):
             from iaf_b200 import _lib
             _lib.check(rc)
 
-    def _capture(self, idxs):
-        """One CUDA graph launching steps ``idxs`` back to back; None when --no-graph or capture is unsupported."""
+    def _capture(self, idxs, tail=None):
+        """One CUDA graph launching steps ``idxs`` back to back (then ``tail()``, e.g. the group's scalar reduction);
+        None when --no-graph or capture is unsupported."""
         if not self.use_graph:
             return None
         try:
@@ -379,6 +380,8 @@ class DeviceBench(object):
                 with torch.cuda.graph(graph, stream=gstream):
                     for i in idxs:
                         self.launch(i, torch.cuda.current_stream(self.device))
+                    if tail is not None:
+                        tail()
             self.stream.wait_stream(gstream)
             return graph
         except Exception as e:  # capture unsupported -> direct launches (still the CUDA path)
@@ -429,25 +432,27 @@ class DeviceBench(object):
         log-dets) and one all-reduce of it across ranks on a side stream.  Returns (seconds per step, launches, scalar)."""
         E, nsets = self.E, self.nsets
         groups = [(s, min(E, K - s)) for s in range(0, K, E)]
-        graphs = {}
-        for s, n in groups:
-            key = (s % nsets, n)
-            if key not in graphs:
-                graphs[key] = self._capture(range(s, s + n))
         scal = torch.zeros((len(groups),), device=self.device)
         rows = self.op.logdets
+
+        def reduce_group(gi, s, n):  # the ELBO term of this evaluation on this rank's shard
+            r0 = s % nsets
+            torch.sum(rows[r0:r0 + n].reshape(-1), dim=0, out=scal[gi])
+        reduce_group(0, 0, groups[0][1])  # outside any capture first (lazy initialisation of the reduction)
+        # one graph per ELBO evaluation: its E step launches and the reduction of their log-dets into scal[gi]
+        graphs = [self._capture(range(s, s + n), tail=(lambda gi=gi, s=s, n=n: reduce_group(gi, s, n)))
+                  for gi, (s, n) in enumerate(groups)]
 
         def run():
             works = []
             for gi, (s, n) in enumerate(groups):
-                g = graphs[(s % nsets, n)]
+                g = graphs[gi]
                 if g is not None:
                     g.replay()
                 else:
                     for i in range(s, s + n):
                         self.launch(i, self.stream)
-                r0 = s % nsets
-                torch.sum(rows[r0:r0 + n].reshape(-1), dim=0, out=scal[gi])  # the ELBO term of this evaluation on this rank's shard
+                    reduce_group(gi, s, n)
                 if self.dist is not None:
                     self.side.wait_stream(self.stream)
                     with torch.cuda.stream(self.side):

@@ -1057,7 +1057,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
 struct TcPackLayer {
   const float* w; const float* scale; const float* bias;
   __nv_bfloat16* whi; __nv_bfloat16* wlo; float* bias_out; float* padw_out;
-  int cin, cout, N, zerodiag, head, is_head;
+  int cin, cout, N, zerodiag, head, is_head, merged;
 };
 struct TcPackParams {
   TcPackLayer layer[IAF_MAX_HIDDEN + IAF_MAX_HEADS];
@@ -1124,7 +1124,7 @@ __global__ void __launch_bounds__(128) iaf_tc_pack_kernel(const __grid_constant_
       const __half lh = __float2half_rn(vc - __half2float(hh));
       const __nv_bfloat16 h = __ushort_as_bfloat16(__half_as_ushort(hh));  // raw 16-bit patterns travel in the bf16-typed images
       const __nv_bfloat16 l = __ushort_as_bfloat16(__half_as_ushort(lh));
-      if (p.korder) {  // layered kernel: separate hi / lo images [K/8][N][8]
+      if (p.korder && !L.merged) {  // layered kernel: separate hi / lo images [K/8][N][8] (merged heads: the interleaved one)
         const size_t o = ((size_t)(k >> 3) * L.N + col) * 8 + (k & 7);
         L.whi[o] = h;
         L.wlo[o] = l;
@@ -1169,7 +1169,7 @@ struct IafTcPlan {
   bool layered;
   int ly_stage[IAF_MAX_STAGES];
   int ly_NB[IAF_MAX_STAGES], ly_sm_a[IAF_MAX_STAGES], ly_sm_b[IAF_MAX_STAGES], ly_sm_bias[IAF_MAX_STAGES],
-      ly_sm_part[IAF_MAX_STAGES], ly_tmem[IAF_MAX_STAGES];
+      ly_sm_part[IAF_MAX_STAGES], ly_tmem[IAF_MAX_STAGES], ly_merged[IAF_MAX_STAGES];
   size_t ly_smem[IAF_MAX_STAGES];
   __nv_bfloat16* img[2][2];  // ping-pong operand images: [which][hi|lo]
   int img_S_pad;
@@ -1470,8 +1470,12 @@ static bool ly_layout(const iaf_desc_t* d, IafTcPlan* pl) {
     q->ly_NB[j] = std::min(nb, LY_MAX_NB);
     q->ly_smem[j] = (size_t)off + (size_t)q->ly_NB[j] * slot;
     if (2 * q->N[j] > 512) return false;
+    // heads stage: hi * [hi | lo] as one N' = 2N MMA when the doubled, double-buffered accumulator fits (N <= 128)
+    const char* me = getenv("IAF_LY_MERGED");
+    q->ly_merged[j] = (j == nst - 1 && 2 * q->N[j] <= 256 && 4 * q->N[j] <= 512 && !(me && me[0] == '0')) ? 1 : 0;
+    const int accw = q->ly_merged[j] ? 2 * q->N[j] : q->N[j];
     int tc = 32;
-    while (tc < 2 * q->N[j]) tc *= 2;
+    while (tc < 2 * accw) tc *= 2;
     q->ly_tmem[j] = tc;
   }
   return true;
@@ -1569,6 +1573,7 @@ int iaf_tc_pack(IafTcPlan* pl, const float* const* w, const float* const* scale,
     L.zerodiag = is_head ? 1 : 0;
     L.is_head = is_head ? 1 : 0;
     L.head = is_head ? i - d.n_hidden : 0;
+    L.merged = pl->layered ? pl->ly_merged[j] : 0;
     max_cout = std::max(max_cout, L.cout);
   }
   dim3 grid(max_cout, pp.n_layers);
@@ -1749,6 +1754,7 @@ int iaf_tc_run(IafTcPlan* pl, const IafTcArgs* a, cudaStream_t stream, int* n_la
       q.S_pad = pl->img_S_pad;
       q.in_mode = j ? 1 : 0;
       q.stage_id = j;
+      q.merged = pl->ly_merged[j];
       // A-operand collector for the (A_hi x B_lo, A_hi x B_hi) pair of every tap: measured C2b 117.4 -> 115.2 us, C3 36.9 -> 36.3 us
       // (profiles/r2_mma_collector.log; the "liar" test there shows the second MMA really takes A from the collector).
       { const char* ce = getenv("IAF_LY_COLLECTOR"); q.collector = ce ? atoi(ce) : 1; }

@@ -88,6 +88,7 @@ struct IafLyParams {
   int n_bchunks;               // weight chunks per tile
   int tl_enable;               // timeline builds only: this launch flushes its events
   int cs;                      // cluster size (1, 2 or 4): CTAs sharing the weight stream by TMA multicast
+  int merged;                  // heads stage: A_hi x [B_hi | B_lo] as ONE N' = 2N MMA (weights image [K/8][2N][8]); accumulator 2N columns
   int collector;               // 1: the hi*lo / hi*hi pair of a tap shares ONE shared-memory fetch of A_hi (A collector)
   int stage_id;                // which conv stage of the stack this launch is (probe / timeline builds)
 };
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) iaf_ly_kernel(const __grid_cons
   const int cfirst = (int)blockIdx.x - crank;  // first CTA of my cluster
   const int n_my = (p.NT - cfirst + (int)gridDim.x - 1) / (int)gridDim.x;
   const uint16_t cmask = (uint16_t)((1u << cs) - 1u);
-  const int acc_cols = St.N;
+  const int acc_cols = q.merged ? 2 * St.N : St.N;
   const bool resident = q.n_bchunks <= q.NB;
 
   // programmatic dependent launch (see iaf_tc_kernel): everything up to the barrier init overlaps the previous grid
@@ -189,7 +190,17 @@ __global__ void __launch_bounds__(LY_THREADS, 1) iaf_ly_kernel(const __grid_cons
           } else {
             mbar_expect_tx(&bars[LB_BFULL + stg], (uint32_t)(2 * q.b_chunk_bytes));
           }
-          if (cs == 1) {
+          if (q.merged) {
+            // interleaved image: the [hi | lo] planes of K-step c are one contiguous run of 2 * b_chunk_bytes
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(St.whi) + 2 * bo;
+            if (cs == 1) {
+              bulk_g2s(dst, src, (uint32_t)q.b_chunk_bytes, &bars[LB_BFULL + stg]);
+              bulk_g2s(dst + q.b_chunk_bytes, src + q.b_chunk_bytes, (uint32_t)q.b_chunk_bytes, &bars[LB_BFULL + stg]);
+            } else {
+              const int slice = 2 * q.b_chunk_bytes / cs;
+              bulk_g2s_mcast(dst + crank * slice, src + crank * slice, (uint32_t)slice, &bars[LB_BFULL + stg], cmask);
+            }
+          } else if (cs == 1) {
             bulk_g2s(dst, reinterpret_cast<const uint8_t*>(St.whi) + bo, (uint32_t)q.b_chunk_bytes, &bars[LB_BFULL + stg]);
             bulk_g2s(dst + q.b_chunk_bytes, reinterpret_cast<const uint8_t*>(St.wlo) + bo, (uint32_t)q.b_chunk_bytes,
                      &bars[LB_BFULL + stg]);
@@ -211,8 +222,9 @@ __global__ void __launch_bounds__(LY_THREADS, 1) iaf_ly_kernel(const __grid_cons
   } else if (warp == LY_MMA_WARP) {
     // ===================== MMA issue (convergent warp, one elected lane) =====================
     const uint32_t idesc = umma_idesc(St.N);
+    const uint32_t idesc2 = umma_idesc(2 * St.N);   // merged form only (2N <= 256 checked by the host layout)
     const uint32_t a_base = smem_u32(smem + q.sm_a);
-    const uint32_t b_plane = (uint32_t)St.N * 16u;
+    const uint32_t b_plane = (uint32_t)St.N * 16u * (q.merged ? 2u : 1u);
     // slot shifts of the taps (0,0) (0,+1) (+1,-1) (+1,0) (+1,+1), in 16-byte descriptor units
     const uint32_t sh1 = 1u, sh2 = (uint32_t)(p.Wp - 1), sh3 = (uint32_t)p.Wp, sh4 = (uint32_t)(p.Wp + 1);
     const uint32_t a_kstep = (2u * (uint32_t)a_plane) >> 4, b_tstep = (2u * b_plane) >> 4;
@@ -260,7 +272,16 @@ __global__ void __launch_bounds__(LY_THREADS, 1) iaf_ly_kernel(const __grid_cons
           umma_f16(d_tmem, mk_desc(al0 + (SH)), mk_desc(bh0 + (T) * b_tstep), idesc, (ACC));       \
           umma_f16_afill(d_tmem, mk_desc(ah0 + (SH)), mk_desc(bl0 + (T) * b_tstep), idesc, 1u);    \
           umma_f16_alast(d_tmem, mk_desc(ah0 + (SH)), mk_desc(bh0 + (T) * b_tstep), idesc, 1u);
-          if (q.collector) {
+#define LY_TAP_M(T, SH, ACC)                                                                  \
+          umma_f16(d_tmem, mk_desc(ah0 + (SH)), mk_desc(bh0 + (T) * b_tstep), idesc2, (ACC)); \
+          umma_f16(d_tmem, mk_desc(al0 + (SH)), mk_desc(bh0 + (T) * b_tstep), idesc, 1u);
+          if (q.merged) {  // hi * [hi | lo] in one instruction (columns [N, 2N) collect hi * lo), then lo * hi
+            LY_TAP_M(0u, 0u, acc0)
+            LY_TAP_M(1u, sh1, 1u)
+            LY_TAP_M(2u, sh2, 1u)
+            LY_TAP_M(3u, sh3, 1u)
+            LY_TAP_M(4u, sh4, 1u)
+          } else if (q.collector) {
             LY_TAP_C(0u, 0u, acc0)
             LY_TAP_C(1u, sh1, 1u)
             LY_TAP_C(2u, sh2, 1u)
@@ -275,6 +296,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) iaf_ly_kernel(const __grid_cons
           }
 #undef LY_TAP
 #undef LY_TAP_C
+#undef LY_TAP_M
           if (!res) {
             if (cs == 1) umma_commit(&bars[LB_BEMPTY + stg]);
             else umma_commit_mcast(&bars[LB_BEMPTY + stg], cmask);
@@ -503,7 +525,15 @@ __global__ void __launch_bounds__(LY_THREADS, 1) iaf_ly_kernel(const __grid_cons
           }
           uint32_t r[16];
           tmem_ld16(t_acc + (uint32_t)c0, r);
-          tmem_ld_wait();
+          if (q.merged) {  // the hi * lo partial products sit in columns [N, 2N)
+            uint32_t r2[16];
+            tmem_ld16(t_acc + (uint32_t)(St.N + c0), r2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) + __uint_as_float(r2[e]));
+          } else {
+            tmem_ld_wait();
+          }
           if (MODE == IAF_MODE_LAYER) {
 #pragma unroll
             for (int k_ = 0; k_ < NRED; ++k_) red[k_] = 0.f;
