@@ -571,20 +571,30 @@ __global__ void __launch_bounds__(BW_THREADS, 2) iaf_bwd_wgrad_kernel(const __gr
   }
 }
 
+#define BW_RED_SEG (BW_THREADS / 32)
 __global__ void __launch_bounds__(BW_THREADS) iaf_bwd_reduce_kernel(const float* part, float* out, int n, int NG) {
-  // fixed summation order (8 interleaved partial sums, then a fixed tree): deterministic, and 8 loads in flight per
-  // thread instead of a chain of NG dependent ones
-  for (int i = blockIdx.x * BW_THREADS + threadIdx.x; i < n; i += gridDim.x * BW_THREADS) {
-    float s[8];
+  // One block per 32 outputs, one warp per SEGMENT of the NG split-K partials: warp w sums partials w, w + 8, w + 16, ...
+  // (four interleaved chains, fixed order), then a fixed tree over the 8 segments.  Deterministic; NG / 32 dependent
+  // round trips per thread instead of NG / 8 (C2a's 64x64 layers have NG = 296: 40 us -> a few us per layer).
+  __shared__ float seg_sum[BW_RED_SEG][32];
+  const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  if (i < n) {
+    int g = seg;
+    for (; g + 3 * BW_RED_SEG < NG; g += 4 * BW_RED_SEG) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) s[k] = 0.f;
-    int g = 0;
-    for (; g + 8 <= NG; g += 8) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) s[k] += part[(size_t)(g + k) * n + i];
+      for (int k = 0; k < 4; ++k) s[k] += part[(size_t)(g + k * BW_RED_SEG) * n + i];
     }
-    for (int k = 0; g < NG; ++g, ++k) s[k] += part[(size_t)g * n + i];
-    out[i] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+    for (int k = 0; g < NG; g += BW_RED_SEG, ++k) s[k] += part[(size_t)g * n + i];
+  }
+  seg_sum[seg][lane] = (s[0] + s[1]) + (s[2] + s[3]);
+  __syncthreads();
+  if (seg == 0 && i < n) {
+    float t[BW_RED_SEG];
+#pragma unroll
+    for (int k = 0; k < BW_RED_SEG; ++k) t[k] = seg_sum[k][lane];
+    out[i] = ((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7]));
   }
 }
 
@@ -956,7 +966,7 @@ int iaf_bwd_run(IafBwdPlan* pl, const IafBwdArgs* a, cudaStream_t stream, int* n
       IAF_LAUNCH(iaf_bwd_wgrad_kernel, q.n_cib * q.n_colb * q.NG, BW_THREADS, pl->wg_smem, stream, q);
       if (cudaGetLastError() != cudaSuccess) return IAF_ERR_CUDA;
       const int n = IAF_NTAPS * pl->cin[j] * pl->ncol[j] + 5 * pl->ncol[j];
-      IAF_LAUNCH(iaf_bwd_reduce_kernel, ew_grid((size_t)n), BW_THREADS, 0, stream,
+      IAF_LAUNCH(iaf_bwd_reduce_kernel, (n + 31) / 32, BW_THREADS, 0, stream,
                  (const float*)pl->part, pl->dwp[j], n, pl->NG[j]);
       if (cudaGetLastError() != cudaSuccess) return IAF_ERR_CUDA;
       nl_ += 2;
