@@ -18,6 +18,7 @@
 // load/store), its pad channel a position-dependent bias whose gradient is a masked sum of G.
 // Reductions use fixed-order partial sums (no float atomics): results are run-to-run deterministic.
 #include "iaf_bwd.h"
+#include "iaf_tc.h"
 
 #define BW_THREADS 256
 #define BW_PX 8
@@ -731,6 +732,7 @@ struct IafBwdPlan {
   int num_sms;
   size_t wg_smem; int wg_RB;
   size_t lc_smem_max;
+  IafDgPlan* dg;               // data gradient on the tensor cores (nullptr: exact-fp32 SIMT lconv kernels)
 };
 
 static void bw_free_scratch(IafBwdPlan* pl) {
@@ -793,12 +795,22 @@ int iaf_bwd_plan_create(IafBwdPlan** out, const iaf_desc_t* d, const int* cin, c
     iaf_bwd_plan_destroy(pl);
     return IAF_ERR_CUDA;
   }
+  // data gradient on the tensor cores when every layer fits the layered kernel's stage (channels in multiples of 16,
+  // packed columns == the next layer's input channels); otherwise, and with IAF_BWD_TC=0, the SIMT kernels below
+  pl->dg = nullptr;
+  {
+    bool ok = true;
+    for (int j = 0; j + 1 < pl->n_stages; ++j) ok = ok && pl->ncol[j] == pl->cin[j + 1];
+    if (ok && iaf_dg_plan_create(&pl->dg, d, pl->cin, pl->ncol, pl->n_stages) != IAF_OK) pl->dg = nullptr;
+    cudaGetLastError();
+  }
   *out = pl;
   return IAF_OK;
 }
 
 void iaf_bwd_plan_destroy(IafBwdPlan* pl) {
   if (!pl) return;
+  if (pl->dg) iaf_dg_plan_destroy(pl->dg);
   bw_free_scratch(pl);
   for (int j = 0; j < IAF_MAX_STAGES; ++j)
     if (pl->dwp[j]) cudaFree(pl->dwp[j]);
@@ -972,6 +984,23 @@ int iaf_bwd_run(IafBwdPlan* pl, const IafBwdArgs* a, cudaStream_t stream, int* n
       nl_ += 2;
     }
     // data gradient
+    if (pl->dg) {
+      // tensor cores: the layered kernel's hidden stage on the point-reflected stream with transposed weights (iaf_tc.cu)
+      if (j == last && (st = iaf_dg_begin(pl->dg, Gcur, B, stream)) != IAF_OK) return st;
+      float* Gnext = nullptr;
+      float* outp = g_zin;
+      if (j > 0) {
+        Gnext = (j == 1 && a->g_ctx) ? a->g_ctx : pl->G[j & 1];  // the gradient at a_0 IS the context gradient
+        outp = Gnext;
+      }
+      if ((st = iaf_dg_stage(pl->dg, j, a->w_packed[j], (last - j) & 1, j > 0 ? hcur[j] : nullptr, outp, j > 0 ? 1 : 0, B,
+                             stream)) != IAF_OK)
+        return st;
+      nl_ += (j == last) ? 3 : 2;
+      Gcur = Gnext;
+      g_planes = pl->cin[j];
+      continue;
+    }
     const int cin_pad = bw_round_up(pl->cin[j], 8);
     {
       const int total = IAF_NTAPS * g_planes * cin_pad;

@@ -1813,3 +1813,259 @@ int iaf_tc_run(IafTcPlan* pl, const IafTcArgs* a, cudaStream_t stream, int* n_la
   if (n_launches) *n_launches = 1;
   return cudaGetLastError() == cudaSuccess ? IAF_OK : IAF_ERR_CUDA;
 }
+
+// ------------------------------------------------------------------------------------------
+// Data gradient of the conv stack on the tensor cores (the "layers, top down" loop of iaf_bwd.cu).
+//
+// The transposed conv of layer j IS a hidden stage of iaf_ly_kernel: on the point-reflected stream (flip toggled) the
+// taps of W^T are the same five slot shifts, so the gradient g (planes = the layer's packed output columns) goes in as an
+// operand image, the transposed effective weights [5 * kin] x [cin] are the B operand, and the epilogue multiplies by
+// nl'(h) (from the kept / recomputed activation h) and writes BOTH the fp32 gradient (weight-gradient kernel, context
+// gradient) and the next operand image.  fp16 operand pairs need the gradient in fp16 range: each sample is scaled by a
+// power of two chosen from its own max |g| at the heads (rows of the implicit GEMM are independent, so a per-sample
+// scale is exact to undo and keeps the result independent of the rest of the batch).
+// ------------------------------------------------------------------------------------------
+struct IafDgPlan {
+  iaf_desc_t d;
+  int n_stages;
+  int kin[IAF_MAX_STAGES], nout[IAF_MAX_STAGES];  // dgrad of layer j: input planes (= packed columns of layer j), output channels (= cin of layer j)
+  __nv_bfloat16* whi[IAF_MAX_STAGES];
+  __nv_bfloat16* wlo[IAF_MAX_STAGES];
+  float* zeros;  // bias table of the stages (the kernel adds it; the gradient has none)
+  int sm_bias[IAF_MAX_STAGES], sm_part[IAF_MAX_STAGES], sm_b[IAF_MAX_STAGES], stage[IAF_MAX_STAGES], NB[IAF_MAX_STAGES],
+      tmem[IAF_MAX_STAGES];
+  size_t smem[IAF_MAX_STAGES];
+  int MIR, WIN, MAXS, max_ch;
+  __nv_bfloat16* img[2][2];  // ping-pong operand images [buffer][hi | lo]
+  int img_S_pad, scratch_B;
+  float* amax;               // [B]
+  int num_sms;
+};
+
+__global__ void __launch_bounds__(256) iaf_dg_pack_kernel(const float* __restrict__ w, __nv_bfloat16* whi, __nv_bfloat16* wlo, int cin,
+                                                          int ncol) {
+  // w: effective (masked, normalised) forward weights [tap][cin][ncol] fp32.  B operand of the data gradient: K index
+  // [column / 16][tap][column % 16] (the layered kernel's K order), N index = ci; images [K/8][N][8], fp16 hi / lo.
+  const int total = IAF_NTAPS * cin * ncol;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
+    const int kc = i % ncol;
+    const int ci = (i / ncol) % cin;
+    const int t = i / (ncol * cin);
+    const float vc = fminf(fmaxf(w[i], -65000.f), 65000.f);
+    const __half hh = __float2half_rn(vc);
+    const __half lh = __float2half_rn(vc - __half2float(hh));
+    const int k = ((kc >> 4) * IAF_NTAPS + t) * 16 + (kc & 15);
+    const size_t o = ((size_t)(k >> 3) * cin + ci) * 8 + (k & 7);
+    whi[o] = __ushort_as_bfloat16(__half_as_ushort(hh));
+    wlo[o] = __ushort_as_bfloat16(__half_as_ushort(lh));
+  }
+}
+
+struct IafDgImageParams {
+  const float* g;  // [B][planes][HW]
+  float* amax;     // [B]
+  __nv_bfloat16* o_hi;
+  __nv_bfloat16* o_lo;
+  int planes, H, W, Wp, SPS, HW, S_pad, flip;
+};
+__global__ void __launch_bounds__(256) iaf_dg_image_kernel(const IafDgImageParams p) {
+  // one block per sample: max |g| of the sample, then its slots of the operand image (pad slots as zeros)
+  __shared__ float red[256];
+  const int n = blockIdx.x, tid = threadIdx.x;
+  const float* g = p.g + (size_t)n * p.planes * p.HW;
+  float m = 0.f;
+  for (int i = tid; i < p.planes * p.HW; i += 256) m = fmaxf(m, fabsf(g[i]));
+  red[tid] = m;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (tid < s) red[tid] = fmaxf(red[tid], red[tid + s]);
+    __syncthreads();
+  }
+  m = red[0];
+  if (tid == 0) p.amax[n] = m;
+  const float sc = dg_scale_from_amax(m);
+  const int nchunk = p.planes >> 3;
+  for (int i = tid; i < nchunk * p.SPS; i += 256) {
+    const int c = i / p.SPS, r = i - c * p.SPS;
+    const int y = r / p.Wp, x = r - y * p.Wp;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = 0.f;
+    if (y < p.H && x < p.W) {
+      const int pix = y * p.W + x;
+      const int gp = p.flip ? p.HW - 1 - pix : pix;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = g[(size_t)(c * 8 + e) * p.HW + gp] * sc;
+    }
+    const size_t go = ((size_t)c * p.S_pad + (size_t)n * p.SPS + r) * 8;
+    split_store8(v, reinterpret_cast<uint8_t*>(p.o_hi + go), reinterpret_cast<uint8_t*>(p.o_lo + go));
+  }
+}
+
+void iaf_dg_plan_destroy(IafDgPlan* pl) {
+  if (!pl) return;
+  for (int j = 0; j < IAF_MAX_STAGES; ++j) {
+    if (pl->whi[j]) cudaFree(pl->whi[j]);
+    if (pl->wlo[j]) cudaFree(pl->wlo[j]);
+  }
+  if (pl->zeros) cudaFree(pl->zeros);
+  if (pl->amax) cudaFree(pl->amax);
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b)
+      if (pl->img[a][b]) cudaFree(pl->img[a][b]);
+  delete pl;
+}
+
+int iaf_dg_plan_create(IafDgPlan** out, const iaf_desc_t* d, const int* cin, const int* ncol, int n_stages) {
+  *out = nullptr;
+  const char* env = getenv("IAF_BWD_TC");
+  if (env && env[0] == '0') return IAF_ERR_UNSUPPORTED;
+  int dev = 0;
+  cudaDeviceProp prop;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return IAF_ERR_CUDA;
+  if (prop.major != 10) return IAF_ERR_UNSUPPORTED;
+  const int Wp = d->W + 1;
+  const int SPS = (d->H + 1) * Wp;
+  const int MIR = tc_round_up(Wp + 1, 8);
+  if (MIR > TC_TILE || n_stages > IAF_MAX_STAGES) return IAF_ERR_UNSUPPORTED;
+  IafDgPlan* pl = new (std::nothrow) IafDgPlan();
+  if (!pl) return IAF_ERR_BAD_ARG;
+  memset(pl, 0, sizeof(*pl));
+  pl->d = *d;
+  pl->n_stages = n_stages;
+  pl->MIR = MIR; pl->WIN = TC_TILE + MIR; pl->MAXS = (TC_TILE - 1) / SPS + 2;
+  pl->num_sms = prop.multiProcessorCount;
+  int maxn = 0;
+  for (int j = 0; j < n_stages; ++j) {
+    const int kin = ncol[j], N = cin[j];
+    pl->kin[j] = kin; pl->nout[j] = N;
+    pl->max_ch = std::max(pl->max_ch, std::max(kin, N));
+    maxn = std::max(maxn, N);
+    if (kin % 16 || N % 16 || kin > 16 * LY_MAX_KS || N > 256 || N < 16) { iaf_dg_plan_destroy(pl); return IAF_ERR_UNSUPPORTED; }
+    int off = 0;
+    pl->sm_bias[j] = off; off += 5 * N * 4;
+    off = tc_round_up(off, 16);
+    pl->sm_part[j] = off; off += 2 * LY_WORKERS * pl->MAXS * 4;
+    off = tc_round_up(off, 128);
+    pl->sm_b[j] = off;
+    const int slot = 2 * LY_KC * 2 * N * 16 + 4 * pl->WIN * 16;  // weight chunk hi+lo + A chunk pair hi+lo
+    pl->stage[j] = slot;
+    const int nb = (TC_SMEM_LIMIT - off) / slot;
+    if (nb < 2) { iaf_dg_plan_destroy(pl); return IAF_ERR_UNSUPPORTED; }
+    pl->NB[j] = std::min(nb, LY_MAX_NB);
+    pl->smem[j] = (size_t)off + (size_t)pl->NB[j] * slot;
+    int tc = 32;
+    while (tc < 2 * N) tc *= 2;
+    pl->tmem[j] = tc;
+    const size_t wb = (size_t)IAF_NTAPS * kin * N * 2;
+    if (cudaMalloc(&pl->whi[j], wb) != cudaSuccess || cudaMalloc(&pl->wlo[j], wb) != cudaSuccess) {
+      iaf_dg_plan_destroy(pl);
+      return IAF_ERR_CUDA;
+    }
+  }
+  if (cudaMalloc(&pl->zeros, sizeof(float) * 5 * maxn) != cudaSuccess ||
+      cudaMemset(pl->zeros, 0, sizeof(float) * 5 * maxn) != cudaSuccess) {
+    iaf_dg_plan_destroy(pl);
+    return IAF_ERR_CUDA;
+  }
+  if (iaf_smem_optin(ly_kernel_for(false, IAF_MODE_MULTICONV, d->nl == IAF_NL_ELU, d->H * d->W)) != cudaSuccess) {
+    iaf_dg_plan_destroy(pl);
+    return IAF_ERR_CUDA;
+  }
+  *out = pl;
+  return IAF_OK;
+}
+
+static int dg_ensure_scratch(IafDgPlan* pl, int B) {
+  if (B <= pl->scratch_B) return IAF_OK;
+  const int SPS = (pl->d.H + 1) * (pl->d.W + 1);
+  if ((long long)B * SPS + TC_TILE >= (1LL << 31)) return IAF_ERR_UNSUPPORTED;
+  const int NT = (B * SPS + TC_TILE - 1) / TC_TILE;
+  pl->img_S_pad = (NT + 1) * TC_TILE;  // one zero tile past the end: windows of the last tile read into it
+  const size_t bytes = (size_t)(pl->max_ch / 8) * pl->img_S_pad * 16;
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b) {
+      if (pl->img[a][b]) cudaFree(pl->img[a][b]);
+      pl->img[a][b] = nullptr;
+      if (cudaMalloc(&pl->img[a][b], bytes) != cudaSuccess) return IAF_ERR_CUDA;
+      if (cudaMemset(pl->img[a][b], 0, bytes) != cudaSuccess) return IAF_ERR_CUDA;
+    }
+  if (pl->amax) cudaFree(pl->amax);
+  pl->amax = nullptr;
+  if (cudaMalloc(&pl->amax, sizeof(float) * (size_t)B) != cudaSuccess) return IAF_ERR_CUDA;
+  pl->scratch_B = B;
+  return IAF_OK;
+}
+
+// gradient at the heads (fp32 [B][kin[last]][HW]) -> per-sample scale + operand image 0
+int iaf_dg_begin(IafDgPlan* pl, const float* g_heads, int B, cudaStream_t stream) {
+  const iaf_desc_t& d = pl->d;
+  int st = dg_ensure_scratch(pl, B);
+  if (st != IAF_OK) return st;
+  IafDgImageParams q;
+  memset(&q, 0, sizeof(q));
+  q.g = g_heads; q.amax = pl->amax; q.o_hi = pl->img[0][0]; q.o_lo = pl->img[0][1];
+  q.planes = pl->kin[pl->n_stages - 1]; q.H = d.H; q.W = d.W; q.Wp = d.W + 1; q.SPS = (d.H + 1) * (d.W + 1);
+  q.HW = d.H * d.W; q.S_pad = pl->img_S_pad;
+  q.flip = d.variant == IAF_VARIANT_THEANO ? 0 : 1;  // the data gradient runs on the point-reflected stream of the forward
+  iaf_dg_image_kernel<<<B, 256, 0, stream>>>(q);
+  return cudaGetLastError() == cudaSuccess ? IAF_OK : IAF_ERR_CUDA;
+}
+
+// data gradient of layer j: image `in_buf` (kin[j] planes) -> fp32 `out` [B][nout[j]][HW] (x nl'(hprev) when hprev is
+// given; accumulated into `out` when it is not: the stack input) and, when `write_image`, the next operand image
+int iaf_dg_stage(IafDgPlan* pl, int j, const float* w_packed, int in_buf, const float* hprev, float* out, int write_image,
+                 int B, cudaStream_t stream) {
+  const iaf_desc_t& d = pl->d;
+  const int kin = pl->kin[j], N = pl->nout[j];
+  {
+    const int total = IAF_NTAPS * N * kin;
+    iaf_dg_pack_kernel<<<std::min(592, (total + 255) / 256), 256, 0, stream>>>(w_packed, pl->whi[j], pl->wlo[j], N, kin);
+    if (cudaGetLastError() != cudaSuccess) return IAF_ERR_CUDA;
+  }
+  const int SPS = (d.H + 1) * (d.W + 1);
+  const int S = B * SPS;
+  const int NT = (S + TC_TILE - 1) / TC_TILE;
+  IafLyParams q;
+  memset(&q, 0, sizeof(q));
+  IafTcParams& p = q.t;
+  p.ctx = hprev;
+  p.n_stages = 1;
+  IafTcStage& S_ = p.st[0];
+  S_.whi = pl->whi[j]; S_.wlo = pl->wlo[j]; S_.bias = pl->zeros; S_.padw = nullptr;
+  S_.hid_out = out;
+  S_.cin = kin; S_.N = N; S_.K = IAF_NTAPS * kin;
+  S_.w_bytes = S_.K * N * 2;
+  S_.sm_bias = pl->sm_bias[j];
+  p.B = B; p.C = d.n_z; p.H = d.H; p.W = d.W; p.Wp = d.W + 1; p.SPS = SPS; p.HW = d.H * d.W;
+  p.S = S; p.NT = NT;
+  p.MIR = pl->MIR; p.WIN = pl->WIN; p.MAXS = pl->MAXS; p.sm_part = pl->sm_part[j];
+  p.flip = d.variant == IAF_VARIANT_THEANO ? 0 : 1;
+  p.nl = d.nl; p.scale = 0.1f;
+  p.tmem_cols = pl->tmem[j];
+  p.mg_sps = (unsigned)((1ULL << 32) / (unsigned)SPS) + 1u;
+  p.mg_wp = (unsigned)((1ULL << 32) / (unsigned)p.Wp) + 1u;
+  p.mg_win = (unsigned)((1ULL << 32) / (unsigned)p.WIN) + 1u;
+  q.a_hi = pl->img[in_buf][0]; q.a_lo = pl->img[in_buf][1];
+  q.o_hi = write_image ? pl->img[in_buf ^ 1][0] : nullptr;
+  q.o_lo = write_image ? pl->img[in_buf ^ 1][1] : nullptr;
+  q.S_pad = pl->img_S_pad;
+  q.in_mode = 1;
+  q.is_heads = 0;
+  q.first = hprev ? 1 : 0;
+  q.NB = pl->NB[j];
+  q.sm_a = 0; q.sm_b = pl->sm_b[j]; q.sm_bias = pl->sm_bias[j]; q.sm_part = pl->sm_part[j];
+  q.b_chunk_bytes = LY_KC * 2 * N * 16;
+  q.stage_bytes = pl->stage[j];
+  q.n_bchunks = kin / 16;
+  q.cs = 1;
+  q.merged = 0;
+  q.collector = 1;
+  q.stage_id = 3;
+  q.bwd = hprev ? 1 : 2;
+  q.amax = pl->amax;
+  LyKernel lk = ly_kernel_for(false, IAF_MODE_MULTICONV, d.nl == IAF_NL_ELU, d.H * d.W);
+  const int grid = std::min(pl->num_sms, NT);
+  lk<<<grid, LY_THREADS, pl->smem[j], stream>>>(q);
+  return cudaGetLastError() == cudaSuccess ? IAF_OK : IAF_ERR_CUDA;
+}

@@ -91,7 +91,30 @@ struct IafLyParams {
   int merged;                  // heads stage: A_hi x [B_hi | B_lo] as ONE N' = 2N MMA (weights image [K/8][2N][8]); accumulator 2N columns
   int collector;               // 1: the hi*lo / hi*hi pair of a tap shares ONE shared-memory fetch of A_hi (A collector)
   int stage_id;                // which conv stage of the stack this launch is (probe / timeline builds)
+  // data-gradient use of a hidden stage (iaf_dg_run): the input image holds the gradient at this layer's output, scaled
+  // per sample into fp16 range; weights are the transposed effective weights; t.ctx points at the activations h whose
+  // nl' multiplies the result (bwd 1) or is null (bwd 2: gradient at the stack input, ACCUMULATED into hid_out)
+  int bwd;                     // 0 forward, 1 x nl'(h), 2 identity and accumulate
+  const float* amax;           // [B] per-sample max |gradient at the heads| (the scale is 2^(5 - floor(log2 amax)))
 };
+
+// nl'(pre-activation) from the activation h = nl(pre-activation)   (same table as iaf_bwd.cu's bw_nl_grad)
+__device__ __forceinline__ float dg_nl_grad(float h, int nl) {
+  switch (nl) {
+    case IAF_NL_ELU: return h > 0.f ? 1.f : h + 1.f;
+    case IAF_NL_SOFTPLUS: return 1.f - __expf(-h);
+    case IAF_NL_RELU: return h > 0.f ? 1.f : 0.f;
+    case IAF_NL_TANH: return 1.f - h * h;
+    case IAF_NL_LEAKYRELU: return h < 0.f ? 0.01f : 1.f;
+    default: return 1.f;
+  }
+}
+// power-of-two scale that brings a sample's gradient into [32, 64): exact to apply and to undo
+__device__ __forceinline__ float dg_scale_from_amax(float amax) {
+  if (!(amax > 1e-30f) || !(amax < 1e30f)) return 1.0f;
+  const int e = (int)((__float_as_uint(amax) >> 23) & 0xffu) - 127;  // floor(log2(amax)) for normal numbers
+  return __uint_as_float((uint32_t)(127 + 5 - e) << 23);
+}
 
 template <bool PADW, int MODE, int NLT, int THW>
 __global__ void __launch_bounds__(LY_THREADS, 1) iaf_ly_kernel(const __grid_constant__ IafLyParams q) {
@@ -412,6 +435,36 @@ __global__ void __launch_bounds__(LY_THREADS, 1) iaf_ly_kernel(const __grid_cons
           uint32_t r[16];
           tmem_ld16(t_acc + (uint32_t)c0, r);
           tmem_ld_wait();
+          if (q.bwd) {
+            // data gradient: acc = W^T g (scaled units); x nl'(h), evaluated from the activation itself
+            const float sc = si.valid ? dg_scale_from_amax(__ldg(q.amax + si.n)) : 1.0f;
+            const float inv = 1.0f / sc;
+            float vb[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const float a = __uint_as_float(r[e]);
+              const float d = (q.bwd == 1) ? dg_nl_grad(cx[e], p.nl) : 1.0f;
+              vb[e] = si.valid ? a * d : 0.f;
+            }
+            if (St.hid_out && si.valid && u < p.NT) {
+              float* hp = St.hid_out + ((size_t)si.n * St.N + c0) * HW + si.gp;
+              if (q.bwd == 2) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) hp[(size_t)e * HW] += vb[e] * inv;
+              } else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) hp[(size_t)e * HW] = vb[e] * inv;
+              }
+            }
+            if (u < p.NT && q.o_hi) {
+#pragma unroll
+              for (int hch = 0; hch < 2; ++hch) {
+                const size_t go = (((size_t)((c0 >> 3) + hch)) * q.S_pad + (size_t)u * TC_TILE + sl) * 8;
+                split_store8(vb + 8 * hch, reinterpret_cast<uint8_t*>(q.o_hi + go), reinterpret_cast<uint8_t*>(q.o_lo + go));
+              }
+            }
+            continue;
+          }
 #ifdef TC_FAST_EPI
           float v[16];
           if (NLT == IAF_NL_ELU && !PADW) {  // packed-pair arithmetic, see iaf_tc_kernel

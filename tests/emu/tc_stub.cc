@@ -8,3 +8,7 @@ void iaf_tc_plan_destroy(IafTcPlan*) {}
 int iaf_tc_pack(IafTcPlan*, const float* const*, const float* const*, const float* const*, cudaStream_t) { return IAF_ERR_UNSUPPORTED; }
 bool iaf_tc_mode_supported(const IafTcPlan*, int) { return false; }
 int iaf_tc_run(IafTcPlan*, const IafTcArgs*, cudaStream_t, int*) { return IAF_ERR_UNSUPPORTED; }
+int iaf_dg_plan_create(IafDgPlan** out, const iaf_desc_t*, const int*, const int*, int) { *out = nullptr; return IAF_ERR_UNSUPPORTED; }
+void iaf_dg_plan_destroy(IafDgPlan*) {}
+int iaf_dg_begin(IafDgPlan*, const float*, int, cudaStream_t) { return IAF_ERR_UNSUPPORTED; }
+int iaf_dg_stage(IafDgPlan*, int, const float*, int, const float*, float*, int, int, cudaStream_t) { return IAF_ERR_UNSUPPORTED; }
