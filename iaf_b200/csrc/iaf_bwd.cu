@@ -573,7 +573,7 @@ __global__ void __launch_bounds__(BW_THREADS, 2) iaf_bwd_wgrad_kernel(const __gr
 }
 
 #define BW_RED_SEG (BW_THREADS / 32)
-__global__ void __launch_bounds__(BW_THREADS) iaf_bwd_reduce_kernel(const float* part, float* out, int n, int NG) {
+__global__ void __launch_bounds__(BW_THREADS) iaf_bwd_reduce_kernel(const float* part, float* out, int n, int NG, int stride) {
   // One block per 32 outputs, one warp per SEGMENT of the NG split-K partials: warp w sums partials w, w + 8, w + 16, ...
   // (four interleaved chains, fixed order), then a fixed tree over the 8 segments.  Deterministic; NG / 32 dependent
   // round trips per thread instead of NG / 8 (C2a's 64x64 layers have NG = 296: 40 us -> a few us per layer).
@@ -585,9 +585,9 @@ __global__ void __launch_bounds__(BW_THREADS) iaf_bwd_reduce_kernel(const float*
     int g = seg;
     for (; g + 3 * BW_RED_SEG < NG; g += 4 * BW_RED_SEG) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) s[k] += part[(size_t)(g + k * BW_RED_SEG) * n + i];
+      for (int k = 0; k < 4; ++k) s[k] += part[(size_t)(g + k * BW_RED_SEG) * stride + i];
     }
-    for (int k = 0; g < NG; g += BW_RED_SEG, ++k) s[k] += part[(size_t)g * n + i];
+    for (int k = 0; g < NG; g += BW_RED_SEG, ++k) s[k] += part[(size_t)g * stride + i];
   }
   seg_sum[seg][lane] = (s[0] + s[1]) + (s[2] + s[3]);
   __syncthreads();
@@ -597,6 +597,58 @@ __global__ void __launch_bounds__(BW_THREADS) iaf_bwd_reduce_kernel(const float*
     for (int k = 0; k < BW_RED_SEG; ++k) t[k] = seg_sum[k][lane];
     out[i] = ((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7]));
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// Bias and pad-channel gradients of one layer when the weight gradient runs on the tensor cores (iaf_wg_kernel does the
+// [5][cin][ncol] part only): out[t][col] = sum over samples and pixels of g * {1, [x = W-1], [y = H-1 or x = 0], [y = H-1],
+// [y = H-1 or x = W-1]} -- the same five sums iaf_bwd_wgrad_kernel's `side` threads form.  One block per column, fixed order.
+// ------------------------------------------------------------------------------------------
+#define BW_BIAS_SEG 32
+__global__ void __launch_bounds__(BW_THREADS) iaf_bwd_bias_kernel(const float* g, float* bpart, int B, int planes, int ncol, int H,
+                                                                  int W, int flip) {
+  // block (column, batch segment): partial sums of its samples -> bpart[segment][5][ncol]; iaf_bwd_reduce_kernel adds the segments
+  __shared__ float red[5][BW_THREADS];
+  const int col = blockIdx.x % ncol, seg = blockIdx.x / ncol, tid = threadIdx.x, HW = H * W;
+  const int n0 = (int)((long long)B * seg / BW_BIAS_SEG), n1 = (int)((long long)B * (seg + 1) / BW_BIAS_SEG);
+  float s[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  const BwDiv dHW = bw_mkdiv(HW), dW = bw_mkdiv(W);
+  const int total = (n1 - n0) * HW;
+  for (int i0 = 0; i0 < total; i0 += 4 * BW_THREADS) {
+    float v[4];
+    int px[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {  // four loads in flight per thread
+      const int i = i0 + k * BW_THREADS + tid;
+      v[k] = 0.f; px[k] = 0;
+      if (i < total) {
+        const int nl = bw_div(i, dHW), pix = i - nl * HW;
+        px[k] = pix;
+        v[k] = g[((size_t)(n0 + nl) * planes + col) * HW + (flip ? HW - 1 - pix : pix)];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int y = bw_div(px[k], dW), x = px[k] - y * W;
+      const bool byH = (y == H - 1), bx0 = (x == 0), bxW = (x == W - 1);
+      s[0] += v[k];
+      s[1] += bxW ? v[k] : 0.f;
+      s[2] += (byH || bx0) ? v[k] : 0.f;
+      s[3] += byH ? v[k] : 0.f;
+      s[4] += (byH || bxW) ? v[k] : 0.f;
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 5; ++t) red[t][tid] = s[t];
+  __syncthreads();
+  for (int st = BW_THREADS / 2; st > 0; st >>= 1) {
+    if (tid < st) {
+#pragma unroll
+      for (int t = 0; t < 5; ++t) red[t][tid] += red[t][tid + st];
+    }
+    __syncthreads();
+  }
+  if (tid < 5) bpart[((size_t)seg * 5 + tid) * ncol + col] = red[tid][0];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -733,6 +785,8 @@ struct IafBwdPlan {
   size_t wg_smem; int wg_RB;
   size_t lc_smem_max;
   IafDgPlan* dg;               // data gradient on the tensor cores (nullptr: exact-fp32 SIMT lconv kernels)
+  int wg_tc;                   // weight gradient on the tensor cores too (IAF_BWD_WG_TC=0: the SIMT kernel)
+  float* bpart;                // [BW_BIAS_SEG][5][max ncol]: bias / pad-channel partial sums of that path
 };
 
 static void bw_free_scratch(IafBwdPlan* pl) {
@@ -803,6 +857,13 @@ int iaf_bwd_plan_create(IafBwdPlan** out, const iaf_desc_t* d, const int* cin, c
     for (int j = 0; j + 1 < pl->n_stages; ++j) ok = ok && pl->ncol[j] == pl->cin[j + 1];
     if (ok && iaf_dg_plan_create(&pl->dg, d, pl->cin, pl->ncol, pl->n_stages) != IAF_OK) pl->dg = nullptr;
     cudaGetLastError();
+    const char* we = getenv("IAF_BWD_WG_TC");
+    pl->wg_tc = (pl->dg && !(we && we[0] == '0')) ? 1 : 0;
+    if (pl->wg_tc) {
+      int mc = 0;
+      for (int j = 0; j < pl->n_stages; ++j) mc = std::max(mc, pl->ncol[j]);
+      if (cudaMalloc(&pl->bpart, sizeof(float) * BW_BIAS_SEG * 5 * mc) != cudaSuccess) { pl->bpart = nullptr; pl->wg_tc = 0; cudaGetLastError(); }
+    }
   }
   *out = pl;
   return IAF_OK;
@@ -811,6 +872,7 @@ int iaf_bwd_plan_create(IafBwdPlan** out, const iaf_desc_t* d, const int* cin, c
 void iaf_bwd_plan_destroy(IafBwdPlan* pl) {
   if (!pl) return;
   if (pl->dg) iaf_dg_plan_destroy(pl->dg);
+  if (pl->bpart) cudaFree(pl->bpart);
   bw_free_scratch(pl);
   for (int j = 0; j < IAF_MAX_STAGES; ++j)
     if (pl->dwp[j]) cudaFree(pl->dwp[j]);
@@ -968,7 +1030,24 @@ int iaf_bwd_run(IafBwdPlan* pl, const IafBwdArgs* a, cudaStream_t stream, int* n
   int g_planes = pl->ncol[last];
   for (int j = last; j >= 0; --j) {
     const float* xin = hcur[j];
-    if (want_params) {
+    if (pl->dg && j == last && (st = iaf_dg_begin(pl->dg, Gcur, B, stream)) != IAF_OK) return st;
+    if (pl->dg && j == last) ++nl_;
+    if (want_params && pl->dg && pl->wg_tc) {
+      // tensor cores: X^T G per tap over the slot stream as K (iaf_wg.cuh); bias / pad-channel sums separately
+      const int nw = IAF_NTAPS * pl->cin[j] * pl->ncol[j];
+      const int n = nw + 5 * pl->ncol[j];
+      int ng = 1;
+      if ((st = iaf_wg_run(pl->dg, j, xin, (last - j) & 1, pl->part, n, pl->NG[j], B, stream, &ng)) != IAF_OK) return st;
+      IAF_LAUNCH(iaf_bwd_reduce_kernel, (nw + 31) / 32, BW_THREADS, 0, stream, (const float*)pl->part, pl->dwp[j], nw, ng, n);
+      if (cudaGetLastError() != cudaSuccess) return IAF_ERR_CUDA;
+      IAF_LAUNCH(iaf_bwd_bias_kernel, pl->ncol[j] * BW_BIAS_SEG, BW_THREADS, 0, stream, Gcur, pl->bpart, B, g_planes, pl->ncol[j],
+                 H, W, flip);
+      if (cudaGetLastError() != cudaSuccess) return IAF_ERR_CUDA;
+      IAF_LAUNCH(iaf_bwd_reduce_kernel, (5 * pl->ncol[j] + 31) / 32, BW_THREADS, 0, stream, (const float*)pl->bpart,
+                 pl->dwp[j] + nw, 5 * pl->ncol[j], BW_BIAS_SEG, 5 * pl->ncol[j]);
+      if (cudaGetLastError() != cudaSuccess) return IAF_ERR_CUDA;
+      nl_ += 5;
+    } else if (want_params) {
       IafWgradParams q;
       memset(&q, 0, sizeof(q));
       q.x = xin; q.g = Gcur; q.part = pl->part;
@@ -979,14 +1058,13 @@ int iaf_bwd_run(IafBwdPlan* pl, const IafBwdArgs* a, cudaStream_t stream, int* n
       if (cudaGetLastError() != cudaSuccess) return IAF_ERR_CUDA;
       const int n = IAF_NTAPS * pl->cin[j] * pl->ncol[j] + 5 * pl->ncol[j];
       IAF_LAUNCH(iaf_bwd_reduce_kernel, (n + 31) / 32, BW_THREADS, 0, stream,
-                 (const float*)pl->part, pl->dwp[j], n, pl->NG[j]);
+                 (const float*)pl->part, pl->dwp[j], n, pl->NG[j], n);
       if (cudaGetLastError() != cudaSuccess) return IAF_ERR_CUDA;
       nl_ += 2;
     }
     // data gradient
     if (pl->dg) {
       // tensor cores: the layered kernel's hidden stage on the point-reflected stream with transposed weights (iaf_tc.cu)
-      if (j == last && (st = iaf_dg_begin(pl->dg, Gcur, B, stream)) != IAF_OK) return st;
       float* Gnext = nullptr;
       float* outp = g_zin;
       if (j > 0) {
@@ -996,7 +1074,7 @@ int iaf_bwd_run(IafBwdPlan* pl, const IafBwdArgs* a, cudaStream_t stream, int* n
       if ((st = iaf_dg_stage(pl->dg, j, a->w_packed[j], (last - j) & 1, j > 0 ? hcur[j] : nullptr, outp, j > 0 ? 1 : 0, B,
                              stream)) != IAF_OK)
         return st;
-      nl_ += (j == last) ? 3 : 2;
+      nl_ += 2;
       Gcur = Gnext;
       g_planes = pl->cin[j];
       continue;

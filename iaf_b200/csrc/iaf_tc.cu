@@ -1048,6 +1048,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) iaf_tc_kernel(const __grid_cons
 }
 
 #include "iaf_tc_gemm.cuh"
+#include "iaf_wg.cuh"
 #include "iaf_fz.cuh"
 
 // ------------------------------------------------------------------------------------------
@@ -1837,6 +1838,7 @@ struct IafDgPlan {
   size_t smem[IAF_MAX_STAGES];
   int MIR, WIN, MAXS, max_ch;
   __nv_bfloat16* img[2][2];  // ping-pong operand images [buffer][hi | lo]
+  __nv_bfloat16* ximg[2];    // weight gradient: operand image of the current layer's input [hi | lo]
   int img_S_pad, scratch_B;
   float* amax;               // [B]
   int num_sms;
@@ -1867,6 +1869,7 @@ struct IafDgImageParams {
   __nv_bfloat16* o_hi;
   __nv_bfloat16* o_lo;
   int planes, H, W, Wp, SPS, HW, S_pad, flip;
+  int xmode, B;    // xmode 1: `g` is a layer INPUT for the weight gradient: scale c / s_n from the amax array (read only)
 };
 __global__ void __launch_bounds__(256) iaf_dg_image_kernel(const IafDgImageParams p) {
   // one block per sample: max |g| of the sample, then its slots of the operand image (pad slots as zeros)
@@ -1874,7 +1877,11 @@ __global__ void __launch_bounds__(256) iaf_dg_image_kernel(const IafDgImageParam
   const int n = blockIdx.x, tid = threadIdx.x;
   const float* g = p.g + (size_t)n * p.planes * p.HW;
   float m = 0.f;
-  for (int i = tid; i < p.planes * p.HW; i += 256) m = fmaxf(m, fabsf(g[i]));
+  if (p.xmode) {
+    for (int i = tid; i < p.B; i += 256) m = fmaxf(m, p.amax[i]);  // the largest gradient of the batch
+  } else {
+    for (int i = tid; i < p.planes * p.HW; i += 256) m = fmaxf(m, fabsf(g[i]));
+  }
   red[tid] = m;
   __syncthreads();
   for (int s = 128; s > 0; s >>= 1) {
@@ -1882,11 +1889,16 @@ __global__ void __launch_bounds__(256) iaf_dg_image_kernel(const IafDgImageParam
     __syncthreads();
   }
   m = red[0];
-  if (tid == 0) p.amax[n] = m;
-  const float sc = dg_scale_from_amax(m);
-  const int nchunk = p.planes >> 3;
+  if (tid == 0 && !p.xmode) p.amax[n] = m;
+  // gradient image: s_n.  Input image of the weight gradient: c / s_n with c = the smallest scale of the batch (<= 1, a
+  // power of two), so that every sample's X * G product carries the same factor c
+  const float sc = p.xmode ? dg_scale_from_amax(m) / dg_scale_from_amax(p.amax[n]) : dg_scale_from_amax(m);
+  const int nchunk_all = p.planes >> 3;
+  // gridDim.y splits the chunk planes (input images of the weight gradient: up to 20 planes per sample)
+  const int c_lo = (int)((long long)nchunk_all * blockIdx.y / gridDim.y), c_hi = (int)((long long)nchunk_all * (blockIdx.y + 1) / gridDim.y);
+  const int nchunk = c_hi - c_lo;
   for (int i = tid; i < nchunk * p.SPS; i += 256) {
-    const int c = i / p.SPS, r = i - c * p.SPS;
+    const int c = c_lo + i / p.SPS, r = i % p.SPS;
     const int y = r / p.Wp, x = r - y * p.Wp;
     float v[8];
 #pragma unroll
@@ -1913,6 +1925,8 @@ void iaf_dg_plan_destroy(IafDgPlan* pl) {
   for (int a = 0; a < 2; ++a)
     for (int b = 0; b < 2; ++b)
       if (pl->img[a][b]) cudaFree(pl->img[a][b]);
+  for (int a = 0; a < 2; ++a)
+    if (pl->ximg[a]) cudaFree(pl->ximg[a]);
   delete pl;
 }
 
@@ -1968,10 +1982,12 @@ int iaf_dg_plan_create(IafDgPlan** out, const iaf_desc_t* d, const int* cin, con
     iaf_dg_plan_destroy(pl);
     return IAF_ERR_CUDA;
   }
-  if (iaf_smem_optin(ly_kernel_for(false, IAF_MODE_MULTICONV, d->nl == IAF_NL_ELU, d->H * d->W)) != cudaSuccess) {
+  if (iaf_smem_optin(ly_kernel_for(false, IAF_MODE_MULTICONV, d->nl == IAF_NL_ELU, d->H * d->W)) != cudaSuccess ||
+      iaf_smem_optin(iaf_wg_kernel) != cudaSuccess) {
     iaf_dg_plan_destroy(pl);
     return IAF_ERR_CUDA;
   }
+  if (Wp + 1 > WG_HALO) { iaf_dg_plan_destroy(pl); return IAF_ERR_UNSUPPORTED; }
   *out = pl;
   return IAF_OK;
 }
@@ -1990,6 +2006,12 @@ static int dg_ensure_scratch(IafDgPlan* pl, int B) {
       if (cudaMalloc(&pl->img[a][b], bytes) != cudaSuccess) return IAF_ERR_CUDA;
       if (cudaMemset(pl->img[a][b], 0, bytes) != cudaSuccess) return IAF_ERR_CUDA;
     }
+  for (int a = 0; a < 2; ++a) {
+    if (pl->ximg[a]) cudaFree(pl->ximg[a]);
+    pl->ximg[a] = nullptr;
+    if (cudaMalloc(&pl->ximg[a], bytes) != cudaSuccess) return IAF_ERR_CUDA;
+    if (cudaMemset(pl->ximg[a], 0, bytes) != cudaSuccess) return IAF_ERR_CUDA;
+  }
   if (pl->amax) cudaFree(pl->amax);
   pl->amax = nullptr;
   if (cudaMalloc(&pl->amax, sizeof(float) * (size_t)B) != cudaSuccess) return IAF_ERR_CUDA;
@@ -2008,6 +2030,7 @@ int iaf_dg_begin(IafDgPlan* pl, const float* g_heads, int B, cudaStream_t stream
   q.planes = pl->kin[pl->n_stages - 1]; q.H = d.H; q.W = d.W; q.Wp = d.W + 1; q.SPS = (d.H + 1) * (d.W + 1);
   q.HW = d.H * d.W; q.S_pad = pl->img_S_pad;
   q.flip = d.variant == IAF_VARIANT_THEANO ? 0 : 1;  // the data gradient runs on the point-reflected stream of the forward
+  q.xmode = 0; q.B = B;
   iaf_dg_image_kernel<<<B, 256, 0, stream>>>(q);
   return cudaGetLastError() == cudaSuccess ? IAF_OK : IAF_ERR_CUDA;
 }
@@ -2067,5 +2090,49 @@ int iaf_dg_stage(IafDgPlan* pl, int j, const float* w_packed, int in_buf, const 
   LyKernel lk = ly_kernel_for(false, IAF_MODE_MULTICONV, d.nl == IAF_NL_ELU, d.H * d.W);
   const int grid = std::min(pl->num_sms, NT);
   lk<<<grid, LY_THREADS, pl->smem[j], stream>>>(q);
+  return cudaGetLastError() == cudaSuccess ? IAF_OK : IAF_ERR_CUDA;
+}
+
+// weight gradient of layer j: X = the layer's input (fp32 [B][nout[j]][HW]), G = operand image `g_buf` (kin[j] planes,
+// the input of data-gradient stage j).  Partials go to part[group][...] (stride part_stride floats); *ng_used groups.
+int iaf_wg_run(IafDgPlan* pl, int j, const float* x, int g_buf, float* part, int part_stride, int ng_max, int B,
+               cudaStream_t stream, int* ng_used) {
+  const iaf_desc_t& d = pl->d;
+  const int cin = pl->nout[j], ncol = pl->kin[j];
+  const int SPS = (d.H + 1) * (d.W + 1);
+  {
+    IafDgImageParams q;
+    memset(&q, 0, sizeof(q));
+    q.g = x; q.amax = pl->amax; q.o_hi = pl->ximg[0]; q.o_lo = pl->ximg[1];
+    q.planes = cin; q.H = d.H; q.W = d.W; q.Wp = d.W + 1; q.SPS = SPS; q.HW = d.H * d.W; q.S_pad = pl->img_S_pad;
+    q.flip = d.variant == IAF_VARIANT_THEANO ? 0 : 1;
+    q.xmode = 1; q.B = B;
+    iaf_dg_image_kernel<<<dim3(B, std::max(1, cin / 32)), 256, 0, stream>>>(q);
+    if (cudaGetLastError() != cudaSuccess) return IAF_ERR_CUDA;
+  }
+  IafWgTcParams q;
+  memset(&q, 0, sizeof(q));
+  q.x_hi = pl->ximg[0]; q.x_lo = pl->ximg[1];
+  q.g_hi = pl->img[g_buf][0]; q.g_lo = pl->img[g_buf][1];
+  q.part = part; q.amax = pl->amax;
+  q.B = B; q.cin = cin; q.ncol = ncol; q.S_pad = pl->img_S_pad; q.Wp = d.W + 1;
+  int Np = 16;
+  for (int c = 16; c <= 96; c += 16)
+    if (ncol % c == 0) Np = c;
+  q.Np = Np; q.n_np = ncol / Np; q.n_mb = (cin + 127) / 128;
+  const int NT = (B * SPS + TC_TILE - 1) / TC_TILE;
+  q.NTK = NT * (TC_TILE / WG_KT);
+  const int ntiles = q.n_mb * q.n_np;
+  q.NG = std::max(1, std::min(std::min(ng_max, q.NTK), pl->num_sms / ntiles));
+  q.part_stride = part_stride;
+  q.xplanes = std::min(16, cin / 8); q.gplanes = Np / 8;
+  q.xa_bytes = 2 * q.xplanes * WG_KT * 16;
+  q.stage_bytes = q.xa_bytes + 2 * q.gplanes * (WG_KT + WG_HALO) * 16;
+  const int slack = 16 * WG_KT * 16 + 1024;  // the M = 128 descriptor walks 16 planes whatever the layer has: stay inside the allocation
+  q.n_stages = std::min(WG_MAX_STAGES, (TC_SMEM_LIMIT - slack) / q.stage_bytes);
+  if (q.n_stages < 2) return IAF_ERR_UNSUPPORTED;
+  const size_t smem = (size_t)q.n_stages * q.stage_bytes + slack;
+  iaf_wg_kernel<<<ntiles * q.NG, WG_THREADS, smem, stream>>>(q);
+  if (ng_used) *ng_used = q.NG;
   return cudaGetLastError() == cudaSuccess ? IAF_OK : IAF_ERR_CUDA;
 }

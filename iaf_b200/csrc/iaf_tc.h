@@ -36,3 +36,5 @@ void iaf_dg_plan_destroy(IafDgPlan* p);
 int iaf_dg_begin(IafDgPlan* p, const float* g_heads, int B, cudaStream_t stream);
 int iaf_dg_stage(IafDgPlan* p, int j, const float* w_packed, int in_buf, const float* hprev, float* out, int write_image,
                  int B, cudaStream_t stream);
+int iaf_wg_run(IafDgPlan* p, int j, const float* x, int g_buf, float* part, int part_stride, int ng_max, int B,
+               cudaStream_t stream, int* ng_used);

@@ -12,3 +12,4 @@ int iaf_dg_plan_create(IafDgPlan** out, const iaf_desc_t*, const int*, const int
 void iaf_dg_plan_destroy(IafDgPlan*) {}
 int iaf_dg_begin(IafDgPlan*, const float*, int, cudaStream_t) { return IAF_ERR_UNSUPPORTED; }
 int iaf_dg_stage(IafDgPlan*, int, const float*, int, const float*, float*, int, int, cudaStream_t) { return IAF_ERR_UNSUPPORTED; }
+int iaf_wg_run(IafDgPlan*, int, const float*, int, float*, int, int, int, cudaStream_t, int*) { return IAF_ERR_UNSUPPORTED; }
