@@ -51,6 +51,7 @@ SYMBOLS = {
     "iaf_version": (C.c_int, []),
     "iaf_plan_path": (C.c_int, [_P]),
     "iaf_plan_path_for_entry": (C.c_int, [_P, C.c_int]),
+    "iaf_plan_bwd_path": (C.c_int, [_P]),
     "iaf_plan_launch_count": (C.c_uint64, [_P]),
     "iaf_plan_algorithmic_bytes": (C.c_size_t, [_P, C.c_int]),
     "iaf_plan_algorithmic_flops": (C.c_double, [_P, C.c_int]),

@@ -604,21 +604,26 @@ __global__ void __launch_bounds__(BW_THREADS) iaf_bwd_reduce_kernel(const float*
 // [5][cin][ncol] part only): out[t][col] = sum over samples and pixels of g * {1, [x = W-1], [y = H-1 or x = 0], [y = H-1],
 // [y = H-1 or x = W-1]} -- the same five sums iaf_bwd_wgrad_kernel's `side` threads form.  One block per column, fixed order.
 // ------------------------------------------------------------------------------------------
-#define BW_BIAS_SEG 32
+#define BW_BIAS_SEG 16
+#ifndef IAF_EMU  // tensor-core path only (never taken under host emulation): warp shuffles
+template <bool PADW>
 __global__ void __launch_bounds__(BW_THREADS) iaf_bwd_bias_kernel(const float* g, float* bpart, int B, int planes, int ncol, int H,
                                                                   int W, int flip) {
-  // block (column, batch segment): partial sums of its samples -> bpart[segment][5][ncol]; iaf_bwd_reduce_kernel adds the segments
-  __shared__ float red[5][BW_THREADS];
+  // block (column, batch segment): partial sums of its samples -> bpart[segment][5][ncol]; iaf_bwd_reduce_kernel adds the
+  // segments.  Fixed order: per-thread strided sums, xor-shuffle tree inside a warp, the 8 warps in index order.
+  // PADW = false (TF numerics): only the plain sum is needed, the pad-channel rows are written as zeros.
+  constexpr int NS = PADW ? 5 : 1;
+  __shared__ float red[BW_THREADS / 32][5];
   const int col = blockIdx.x % ncol, seg = blockIdx.x / ncol, tid = threadIdx.x, HW = H * W;
   const int n0 = (int)((long long)B * seg / BW_BIAS_SEG), n1 = (int)((long long)B * (seg + 1) / BW_BIAS_SEG);
   float s[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
   const BwDiv dHW = bw_mkdiv(HW), dW = bw_mkdiv(W);
   const int total = (n1 - n0) * HW;
-  for (int i0 = 0; i0 < total; i0 += 4 * BW_THREADS) {
-    float v[4];
-    int px[4];
+  for (int i0 = 0; i0 < total; i0 += 8 * BW_THREADS) {
+    float v[8];
+    int px[8];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {  // four loads in flight per thread
+    for (int k = 0; k < 8; ++k) {  // eight loads in flight per thread
       const int i = i0 + k * BW_THREADS + tid;
       v[k] = 0.f; px[k] = 0;
       if (i < total) {
@@ -628,28 +633,33 @@ __global__ void __launch_bounds__(BW_THREADS) iaf_bwd_bias_kernel(const float* g
       }
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int y = bw_div(px[k], dW), x = px[k] - y * W;
-      const bool byH = (y == H - 1), bx0 = (x == 0), bxW = (x == W - 1);
+    for (int k = 0; k < 8; ++k) {
       s[0] += v[k];
-      s[1] += bxW ? v[k] : 0.f;
-      s[2] += (byH || bx0) ? v[k] : 0.f;
-      s[3] += byH ? v[k] : 0.f;
-      s[4] += (byH || bxW) ? v[k] : 0.f;
+      if (PADW) {
+        const int y = bw_div(px[k], dW), x = px[k] - y * W;
+        const bool byH = (y == H - 1), bx0 = (x == 0), bxW = (x == W - 1);
+        s[1] += bxW ? v[k] : 0.f;
+        s[2] += (byH || bx0) ? v[k] : 0.f;
+        s[3] += byH ? v[k] : 0.f;
+        s[4] += (byH || bxW) ? v[k] : 0.f;
+      }
     }
   }
 #pragma unroll
-  for (int t = 0; t < 5; ++t) red[t][tid] = s[t];
+  for (int t = 0; t < NS; ++t)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s[t] += __shfl_xor_sync(0xffffffffu, s[t], o);
+  if ((tid & 31) == 0)
+#pragma unroll
+    for (int t = 0; t < 5; ++t) red[tid >> 5][t] = s[t];
   __syncthreads();
-  for (int st = BW_THREADS / 2; st > 0; st >>= 1) {
-    if (tid < st) {
-#pragma unroll
-      for (int t = 0; t < 5; ++t) red[t][tid] += red[t][tid + st];
-    }
-    __syncthreads();
+  if (tid < 5) {
+    float r = 0.f;
+    for (int w = 0; w < BW_THREADS / 32; ++w) r += red[w][tid];
+    bpart[((size_t)seg * 5 + tid) * ncol + col] = r;
   }
-  if (tid < 5) bpart[((size_t)seg * 5 + tid) * ncol + col] = red[tid][0];
 }
+#endif
 
 // ------------------------------------------------------------------------------------------
 // dW (packed) -> raw-parameter gradients through the mask and the weight normalisation.  One block per
@@ -805,8 +815,10 @@ static void bw_free_scratch(IafBwdPlan* pl) {
   pl->scratch_B = 0;
 }
 
+int iaf_bwd_plan_uses_tc(const IafBwdPlan* p) { return !p || !p->dg ? 0 : (p->wg_tc ? 2 : 1); }
+
 int iaf_bwd_plan_create(IafBwdPlan** out, const iaf_desc_t* d, const int* cin, const int* cout, const int* cout_pad,
-                        int head_pad) {
+                        int head_pad, int allow_tc) {
   IafBwdPlan* pl = new (std::nothrow) IafBwdPlan();
   if (!pl) return IAF_ERR_BAD_ARG;
   memset(pl, 0, sizeof(*pl));
@@ -853,7 +865,7 @@ int iaf_bwd_plan_create(IafBwdPlan** out, const iaf_desc_t* d, const int* cin, c
   // packed columns == the next layer's input channels); otherwise, and with IAF_BWD_TC=0, the SIMT kernels below
   pl->dg = nullptr;
   {
-    bool ok = true;
+    bool ok = allow_tc != 0;
     for (int j = 0; j + 1 < pl->n_stages; ++j) ok = ok && pl->ncol[j] == pl->cin[j + 1];
     if (ok && iaf_dg_plan_create(&pl->dg, d, pl->cin, pl->ncol, pl->n_stages) != IAF_OK) pl->dg = nullptr;
     cudaGetLastError();
@@ -1040,8 +1052,10 @@ int iaf_bwd_run(IafBwdPlan* pl, const IafBwdArgs* a, cudaStream_t stream, int* n
       if ((st = iaf_wg_run(pl->dg, j, xin, (last - j) & 1, pl->part, n, pl->NG[j], B, stream, &ng)) != IAF_OK) return st;
       IAF_LAUNCH(iaf_bwd_reduce_kernel, (nw + 31) / 32, BW_THREADS, 0, stream, (const float*)pl->part, pl->dwp[j], nw, ng, n);
       if (cudaGetLastError() != cudaSuccess) return IAF_ERR_CUDA;
-      IAF_LAUNCH(iaf_bwd_bias_kernel, pl->ncol[j] * BW_BIAS_SEG, BW_THREADS, 0, stream, Gcur, pl->bpart, B, g_planes, pl->ncol[j],
-                 H, W, flip);
+#ifndef IAF_EMU
+      if (flip) iaf_bwd_bias_kernel<true><<<pl->ncol[j] * BW_BIAS_SEG, BW_THREADS, 0, stream>>>(Gcur, pl->bpart, B, g_planes, pl->ncol[j], H, W, flip);
+      else iaf_bwd_bias_kernel<false><<<pl->ncol[j] * BW_BIAS_SEG, BW_THREADS, 0, stream>>>(Gcur, pl->bpart, B, g_planes, pl->ncol[j], H, W, flip);
+#endif
       if (cudaGetLastError() != cudaSuccess) return IAF_ERR_CUDA;
       IAF_LAUNCH(iaf_bwd_reduce_kernel, (5 * pl->ncol[j] + 31) / 32, BW_THREADS, 0, stream, (const float*)pl->bpart,
                  pl->dwp[j] + nw, 5 * pl->ncol[j], BW_BIAS_SEG, 5 * pl->ncol[j]);

@@ -45,7 +45,10 @@ struct IafBwdArgs {
   float* const* g_bias;
 };
 
+// allow_tc: the plan's forward runs on the tensor-core path, so its backward may too (data gradient as a layered-kernel stage,
+// weight gradient as MN-major MMAs over the slot stream); a plan pinned to the exact-fp32 SIMT path keeps the SIMT backward
 int iaf_bwd_plan_create(IafBwdPlan** out, const iaf_desc_t* d, const int* cin, const int* cout, const int* cout_pad,
-                        int head_pad);
+                        int head_pad, int allow_tc);
+int iaf_bwd_plan_uses_tc(const IafBwdPlan* p);  // 0: SIMT, 1: data gradient on tensor cores, 2: data and weight gradient
 void iaf_bwd_plan_destroy(IafBwdPlan* p);
 int iaf_bwd_run(IafBwdPlan* p, const IafBwdArgs* a, cudaStream_t stream, int* n_launches);

@@ -458,7 +458,7 @@ static int run_bwd(iaf_plan* pl, int mode, const float* z, const float* ctx, con
       if (!w[i] || !scale[i]) return IAF_ERR_BAD_ARG;
   }
   if (!pl->bwd) {
-    int st = iaf_bwd_plan_create(&pl->bwd, &d, pl->cin, pl->cout, pl->cout_pad, pl->head_pad);
+    int st = iaf_bwd_plan_create(&pl->bwd, &d, pl->cin, pl->cout, pl->cout_pad, pl->head_pad, pl->path == IAF_PATH_TC);
     if (st != IAF_OK) return st == IAF_ERR_CUDA ? cuda_fail(cudaGetLastError(), "iaf_bwd_plan_create") : st;
   }
   IafBwdArgs a;
@@ -527,7 +527,7 @@ int iaf_layer_bwd(iaf_plan_t* pl, const float* eps, const float* post_mean, cons
       if (!w[i] || !scale[i]) return IAF_ERR_BAD_ARG;
   }
   if (!pl->bwd) {
-    int st = iaf_bwd_plan_create(&pl->bwd, &d, pl->cin, pl->cout, pl->cout_pad, pl->head_pad);
+    int st = iaf_bwd_plan_create(&pl->bwd, &d, pl->cin, pl->cout, pl->cout_pad, pl->head_pad, pl->path == IAF_PATH_TC);
     if (st != IAF_OK) return st == IAF_ERR_CUDA ? cuda_fail(cudaGetLastError(), "iaf_bwd_plan_create") : st;
   }
   IafBwdArgs a;
@@ -692,6 +692,14 @@ int iaf_plan_path_for_entry(const iaf_plan_t* pl, int entry) {
   if (pl->path == IAF_PATH_TC && iaf_tc_mode_supported(pl->tc, entry)) return IAF_PATH_TC;
   if (pl->path == IAF_PATH_TC && pl->d.path == IAF_PATH_TC) return IAF_ERR_UNSUPPORTED;
   return pl->simt_ok ? IAF_PATH_SIMT : IAF_ERR_UNSUPPORTED;
+}
+int iaf_plan_bwd_path(iaf_plan_t* pl) {
+  if (!pl) return IAF_ERR_BAD_ARG;
+  if (!pl->bwd) {
+    int st = iaf_bwd_plan_create(&pl->bwd, &pl->d, pl->cin, pl->cout, pl->cout_pad, pl->head_pad, pl->path == IAF_PATH_TC);
+    if (st != IAF_OK) return st == IAF_ERR_CUDA ? cuda_fail(cudaGetLastError(), "iaf_bwd_plan_create") : st;
+  }
+  return iaf_bwd_plan_uses_tc(pl->bwd);
 }
 uint64_t iaf_plan_launch_count(const iaf_plan_t* pl) { return pl ? pl->launches : 0; }
 

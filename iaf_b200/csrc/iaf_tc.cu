@@ -2031,7 +2031,8 @@ int iaf_dg_begin(IafDgPlan* pl, const float* g_heads, int B, cudaStream_t stream
   q.HW = d.H * d.W; q.S_pad = pl->img_S_pad;
   q.flip = d.variant == IAF_VARIANT_THEANO ? 0 : 1;  // the data gradient runs on the point-reflected stream of the forward
   q.xmode = 0; q.B = B;
-  iaf_dg_image_kernel<<<B, 256, 0, stream>>>(q);
+  // gridDim.y splits the image planes; every y-block recomputes the sample's max (L2 hits) and writes the same value
+  iaf_dg_image_kernel<<<dim3(B, std::max(1, q.planes / 16)), 256, 0, stream>>>(q);
   return cudaGetLastError() == cudaSuccess ? IAF_OK : IAF_ERR_CUDA;
 }
 

@@ -74,29 +74,32 @@ __global__ void __launch_bounds__(WG_THREADS, 1) iaf_wg_kernel(const __grid_cons
   const uint32_t tmem_base = s_tmem;
 
   if (warp == WG_W_TMA) {
-    if (lane == 0) {
-      const uint32_t tx = (uint32_t)(2 * xpl * x_pitch + 2 * p.gplanes * g_pitch);
-      for (int i = 0; i < n_my; ++i) {
-        const int u = g + i * p.NG;
-        const int stg = i % p.n_stages, use = i / p.n_stages;
-        if (use >= 1) mbar_wait(&empty[stg], (uint32_t)((use - 1) & 1));
-        uint8_t* dst = smem + (size_t)stg * p.stage_bytes;
-        mbar_expect_tx(&full[stg], tx);
-        const size_t s0 = (size_t)u * WG_KT;
-        for (int c = 0; c < xpl; ++c) {
+    // one bulk copy per chunk plane and image; the lanes of the warp issue them side by side
+    const uint32_t tx = (uint32_t)(2 * xpl * x_pitch + 2 * p.gplanes * g_pitch);
+    const int ncp = 2 * xpl + 2 * p.gplanes;
+    for (int i = 0; i < n_my; ++i) {
+      const int u = g + i * p.NG;
+      const int stg = i % p.n_stages, use = i / p.n_stages;
+      if (use >= 1) mbar_wait(&empty[stg], (uint32_t)((use - 1) & 1));
+      uint8_t* dst = smem + (size_t)stg * p.stage_bytes;
+      if (lane == 0) mbar_expect_tx(&full[stg], tx);
+      __syncwarp();
+      const size_t s0 = (size_t)u * WG_KT;
+      for (int k = lane; k < ncp; k += 32) {
+        if (k < 2 * xpl) {
+          const int lo = k >= xpl, c = lo ? k - xpl : k;
           const size_t go = ((size_t)(mb * 16 + c) * p.S_pad + s0) * 8;
-          bulk_g2s(dst + c * x_pitch, p.x_hi + go, (uint32_t)x_pitch, &full[stg]);
-          bulk_g2s(dst + (p.xplanes + c) * x_pitch, p.x_lo + go, (uint32_t)x_pitch, &full[stg]);
-        }
-        uint8_t* dg = dst + p.xa_bytes;
-        for (int c = 0; c < p.gplanes; ++c) {
+          bulk_g2s(dst + ((lo ? p.xplanes : 0) + c) * x_pitch, (lo ? p.x_lo : p.x_hi) + go, (uint32_t)x_pitch, &full[stg]);
+        } else {
+          const int kk = k - 2 * xpl;
+          const int lo = kk >= p.gplanes, c = lo ? kk - p.gplanes : kk;
           const size_t go = ((size_t)(np * (p.Np >> 3) + c) * p.S_pad + s0) * 8;
-          bulk_g2s(dg + c * g_pitch, p.g_hi + go, (uint32_t)g_pitch, &full[stg]);
-          bulk_g2s(dg + (p.gplanes + c) * g_pitch, p.g_lo + go, (uint32_t)g_pitch, &full[stg]);
+          bulk_g2s(dst + p.xa_bytes + ((lo ? p.gplanes : 0) + c) * g_pitch, (lo ? p.g_lo : p.g_hi) + go, (uint32_t)g_pitch,
+                   &full[stg]);
         }
       }
+      __syncwarp();
     }
-    __syncwarp();
   } else if (warp == WG_W_MMA) {
     // instruction descriptor: fp16 x fp16 -> f32, BOTH operands MN-major (bits 15, 16), M = 128, N = Np
     const uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(p.Np >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);

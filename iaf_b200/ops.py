@@ -174,6 +174,14 @@ class IAFOperator(object):
             _lib.check(rc)
         return _lib.PATH_NAMES[rc]
 
+    def backward_path(self, H, W, device):
+        """Kernels behind the backward entries for (H, W): "simt" (exact fp32), "tc-dgrad" (data gradient on the tensor
+        cores) or "tc" (data and weight gradient on the tensor cores)."""
+        rc = self._lib.iaf_plan_bwd_path(self._plan(H, W, torch.device(device)))
+        if rc < 0:
+            _lib.check(rc)
+        return ("simt", "tc-dgrad", "tc")[rc]
+
     def launch_count(self):
         return sum(int(self._lib.iaf_plan_launch_count(e[0])) for e in self._plans.values())
 

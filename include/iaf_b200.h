@@ -224,6 +224,11 @@ int iaf_plan_path(const iaf_plan_t* plan);      /* iaf_path actually selected (S
  * downgrades: that entry returns IAF_ERR_UNSUPPORTED, and so does this function. */
 typedef enum { IAF_ENTRY_MULTICONV = 0, IAF_ENTRY_STEP = 1, IAF_ENTRY_LAYER = 2 } iaf_entry;
 int iaf_plan_path_for_entry(const iaf_plan_t* plan, int entry);
+/* Which kernels the plan's BACKWARD entries run (creates the backward plan on first use): 0 = exact-fp32 SIMT kernels,
+ * 1 = data gradient on the tensor cores, 2 = data and weight gradient on the tensor cores (plans whose forward is on the
+ * tensor-core path, channel counts in multiples of 16; IAF_BWD_TC=0 / IAF_BWD_WG_TC=0 in the environment switch them off).
+ * The reference differentiates the same graph it runs forward (graphy/nodes/ar.py:304-329 through theano.grad). */
+int iaf_plan_bwd_path(iaf_plan_t* plan);
 uint64_t iaf_plan_launch_count(const iaf_plan_t* plan); /* kernels launched through this plan so far    */
 size_t iaf_plan_algorithmic_bytes(const iaf_plan_t* plan, int B); /* SURVEY 8d bytes of one iaf_step_fwd */
 double iaf_plan_algorithmic_flops(const iaf_plan_t* plan, int B); /* 2*B*H*W*sum nnz(mask)              */

@@ -181,3 +181,67 @@ def test_backward_error_behaviour():
     # no gradient requested anywhere: the forward is not recorded
     zo, _, _ = op.step(z, ctx)
     assert not zo.requires_grad
+
+
+@pytest.mark.parametrize("variant,hidden,H,W,nl", [("tf", [64], 16, 16, "elu"), ("theano", [160, 160], 16, 16, "softplus"),
+                                                   ("tf", [160, 160], 8, 8, "elu")],
+                         ids=["c2a", "c4-softplus", "c3-8x8"])
+def test_tensor_core_backward_is_taken_and_matches_the_simt_backward(variant, hidden, H, W, nl, monkeypatch):
+    """The backward of a tensor-core plan runs its data gradient (layered-kernel stage on the point-reflected stream) and
+    its weight gradient (MN-major MMAs over the slot stream) on the tensor cores -- `backward_path` says so -- and agrees
+    with the exact-fp32 SIMT backward of the same operator (IAF_BWD_TC=0) within the parity tolerance; a plan pinned to the
+    SIMT path keeps the SIMT backward."""
+    n_z, B = 32, 5
+    rng = np.random.RandomState(11)
+
+    def grads(env):
+        if env is not None:
+            monkeypatch.setenv("IAF_BWD_TC", env)
+        else:
+            monkeypatch.delenv("IAF_BWD_TC", raising=False)
+        op, dev, _, _, z, ctx = _build(variant, n_z, hidden, [n_z, n_z], H, W, B, nl)
+        path = op.backward_path(H, W, "cuda")
+        zg = torch.from_numpy(z).cuda().requires_grad_(True)
+        cg = torch.from_numpy(ctx).cuda().requires_grad_(True)
+        r = np.random.RandomState(5)
+        gzo, gls = r.randn(*z.shape).astype(np.float32), r.randn(*z.shape).astype(np.float32)
+        gld = r.randn(B).astype(np.float32)
+        zo, ls, ld = op.step(zg, cg)
+        (zo * torch.from_numpy(gzo).cuda()).sum().add((ls * torch.from_numpy(gls).cuda()).sum()).add(
+            (ld * torch.from_numpy(gld).cuda()).sum()).backward()
+        return path, [zg.grad, cg.grad] + [t.grad for l in dev for t in l]
+
+    p_tc, g_tc = grads(None)
+    p_simt, g_simt = grads("0")
+    assert p_tc == "tc" and p_simt == "simt", (p_tc, p_simt)
+    for a, b in zip(g_tc, g_simt):
+        assert torch.isfinite(a).all()
+        assert float((a.double() - b.double()).abs().max()) <= TOL * max(float(b.abs().max()), 1e-30)
+    monkeypatch.delenv("IAF_BWD_TC", raising=False)
+    op = _build(variant, n_z, hidden, [n_z, n_z], H, W, B, nl, path="simt")[0]
+    assert op.backward_path(H, W, "cuda") == "simt"
+    del rng
+
+
+def test_tensor_core_backward_is_scale_invariant():
+    """Gradients 2^-40 and 2^+20 times the usual size go through the fp16 operand images unharmed: every sample is scaled by
+    a power of two taken from its own largest gradient (exact to undo), so the result is the usual one times that factor."""
+    variant, n_z, hidden, H, W, B, nl = "tf", 32, [64], 16, 16, 3, "elu"
+    op, dev, _, _, z, ctx = _build(variant, n_z, hidden, [n_z, n_z], H, W, B, nl)
+    assert op.backward_path(H, W, "cuda") == "tc"
+    r = np.random.RandomState(5)
+    gzo = torch.from_numpy(r.randn(*z.shape).astype(np.float32)).cuda()
+    out = []
+    for f in (1.0, 2.0 ** -40, 2.0 ** 20):
+        zg = torch.from_numpy(z).cuda().requires_grad_(True)
+        cg = torch.from_numpy(ctx).cuda().requires_grad_(True)
+        for l in dev:
+            for t in l:
+                t.grad = None
+        zo, ls, ld = op.step(zg, cg)
+        (zo * (gzo * f)).sum().backward()
+        out.append([zg.grad / f, cg.grad / f] + [t.grad / f for l in dev for t in l])
+    for other in out[1:]:
+        for a, b in zip(out[0], other):
+            assert torch.isfinite(b).all()
+            assert float((a.double() - b.double()).abs().max()) <= 1e-5 * max(float(a.abs().max()), 1e-30)
