@@ -19,7 +19,8 @@ n_z=32, 16x16.  Metric: latent elements/s = 256*n_z*H*W / t_step, wh
                iaf_step_submit_host): pinned host inputs H2D, step, results D2H, every step,
                pipelined over three device staging slots; timed until wait_host() returns.
 * also       : the other headline shape (hidden [160,160]: c2b at N=1, the same batch sharded = c5 at N>1),
-               device-timed in the same run.
+               device-timed in the same run; at N=1 also `training_pair`: forward keeping the activations
+               + backward from them (all gradients) for both shapes, microseconds per call.
 * cpu_baseline / --impl reference: the oracle's torch-CPU port of the reference path on this box's
                cores (the reference's Theano/TF code cannot run in this image).  ONE routine
                serves both: per thread-count candidate 3 warm-up + 5 timed calls (median), the best
@@ -475,6 +476,31 @@ class DeviceBench(object):
         n_launched = direct if direct else K * self.launches_per_step  # graph replays do not pass through the C ABI
         return ms * 1e-3 / K, int(n_launched), float(scal.sum()), len(groups)
 
+    def training_pair(self, iters=20):
+        """Forward that keeps the activations (iaf_step_fwd_train) and backward from them (iaf_step_bwd_saved: gradients of z,
+        context and every parameter), the pair the autograd node of IAFOperator.step runs; CUDA events, this rank's shard."""
+        op, s = self.op, self.sets[0]
+        z, ctx = s["z"], s["ctx"]
+        g1 = torch.randn_like(z)
+        gl = torch.randn(self.B, device=self.device)
+
+        def timed(fn):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / iters * 1e3
+        t_f = timed(lambda: op._step_train_raw(z, ctx))
+        zo, ls, _, hs = op._step_train_raw(z, ctx)
+        t_b = timed(lambda: op._backward("step", z, ctx, op._layers, (g1, g1, gl), True, saved=(zo, ls, hs)))
+        return {"fwd_train_us": t_f, "bwd_saved_us": t_b, "samples": self.B,
+                "backward_path": op.backward_path(self.H, self.W, self.device)}
+
     def roofline(self, t_kernel):
         hbm_gbs, bf16_tf, peak_src = measured_peaks()
         op, H, W, dev = self.op, self.H, self.W, self.device
@@ -618,6 +644,8 @@ def main():
             "value": o_elems / ot_step, "unit": UNIT, "steps": Ko, "ms_per_step": ot_step * 1e3,
             "steps_per_elbo": ob.E, "elbo_evaluations": o_groups, "gpu_launches": on_launched,
             "kernels_per_step": ob.launches_per_step, "roofline": ob.roofline(ot_kernel)}}
+        if world == 1:  # the training pair of both headline shapes, device-timed in the same run
+            also["training_pair"] = {"c2a": db.training_pair(), "c2b": ob.training_pair(10)}
         if sampler:
             sampler.phase = "between"
         del ob
@@ -636,7 +664,7 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f32 (tc path: bf16x3 split operands, f32 accumulate)" if path == "tc" else "f32",
+        "dtype": "f32 (tc path: fp16 hi/lo operand pairs, three products per MAC, f32 accumulate)" if path == "tc" else "f32",
         "data": "synthetic",
         "config": {"workload": workload_string(name), "global_batch": db.Bg, "samples_per_gpu": db.B,
                    "parallelism": "dp%d" % world, "path": path, "launch": db.launch_mode,

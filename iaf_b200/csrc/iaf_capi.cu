@@ -80,6 +80,9 @@ struct iaf_plan {
   IafTcPlan* tc;
   // backward (created on the first iaf_*_bwd call)
   IafBwdPlan* bwd;
+  // recompute of iaf_step_bwd (the entry without kept activations) on the forward's own tensor-core kernels
+  float* rc_zo; float* rc_ls; float* rc_h[IAF_MAX_HIDDEN];
+  int rc_B;
   uint64_t launches;
   // a plan's scratch (partial sums, counters, packed weights, operand images) serves ONE stream at a time: when a call
   // arrives on a different stream than the previous one, the new stream first waits for the old one's work
@@ -298,6 +301,10 @@ void iaf_plan_destroy(iaf_plan_t* pl) {
   if (pl->s_d2h) cudaStreamDestroy(pl->s_d2h);
   if (pl->tc) iaf_tc_plan_destroy(pl->tc);
   if (pl->bwd) iaf_bwd_plan_destroy(pl->bwd);
+  if (pl->rc_zo) cudaFree(pl->rc_zo);
+  if (pl->rc_ls) cudaFree(pl->rc_ls);
+  for (int j = 0; j < IAF_MAX_HIDDEN; ++j)
+    if (pl->rc_h[j]) cudaFree(pl->rc_h[j]);
   delete pl;
 }
 
@@ -475,6 +482,32 @@ static int run_bwd(iaf_plan* pl, int mode, const float* z, const float* ctx, con
   a.z_out_saved = z_out_saved; a.logsd_saved = logsd_saved;
   for (int j = 0; j < d.n_hidden && hidden_saved; ++j) a.h_saved[j] = hidden_saved[j];
   a.have_saved = z_out_saved != nullptr;
+  if (mode == IAF_MODE_STEP && !z_out_saved && pl->path == IAF_PATH_TC && iaf_tc_mode_supported(pl->tc, IAF_MODE_STEP) &&
+      iaf_bwd_plan_uses_tc(pl->bwd)) {
+    // a tensor-core plan recomputes z', arw_logsd and the activations with its own forward (one training-forward call)
+    // instead of the SIMT layer convs: what iaf_step_fwd_train would have kept
+    if (B > pl->rc_B) {
+      const size_t hw = (size_t)d.H * d.W;
+      if (pl->rc_zo) cudaFree(pl->rc_zo);
+      if (pl->rc_ls) cudaFree(pl->rc_ls);
+      pl->rc_zo = pl->rc_ls = nullptr;
+      for (int j = 0; j < IAF_MAX_HIDDEN; ++j) { if (pl->rc_h[j]) cudaFree(pl->rc_h[j]); pl->rc_h[j] = nullptr; }
+      pl->rc_B = 0;
+      if (cudaMalloc(&pl->rc_zo, sizeof(float) * B * d.n_z * hw) != cudaSuccess ||
+          cudaMalloc(&pl->rc_ls, sizeof(float) * B * d.n_z * hw) != cudaSuccess)
+        return cuda_fail(cudaGetLastError(), "recompute scratch");
+      for (int j = 0; j < d.n_hidden; ++j)
+        if (cudaMalloc(&pl->rc_h[j], sizeof(float) * B * d.hidden[j] * hw) != cudaSuccess)
+          return cuda_fail(cudaGetLastError(), "recompute scratch");
+      pl->rc_B = B;
+    }
+    int st = run(pl, IAF_MODE_STEP, z, ctx, nullptr, nullptr, nullptr, nullptr, pl->rc_zo, pl->rc_ls, nullptr, nullptr, nullptr,
+                 nullptr, B, stream, pl->rc_h);
+    if (st != IAF_OK) return st;
+    a.z_out_saved = pl->rc_zo; a.logsd_saved = pl->rc_ls;
+    for (int j = 0; j < d.n_hidden; ++j) a.h_saved[j] = pl->rc_h[j];
+    a.have_saved = 1;
+  }
   int nl = 0;
   int st = iaf_bwd_run(pl->bwd, &a, stream, &nl);
   if (st == IAF_ERR_CUDA) return cuda_fail(cudaGetLastError(), "iaf_bwd_run");

@@ -1869,12 +1869,29 @@ struct IafDgImageParams {
   __nv_bfloat16* o_hi;
   __nv_bfloat16* o_lo;
   int planes, H, W, Wp, SPS, HW, S_pad, flip;
+  int S_end;       // slots [B * SPS, S_end) are zeroed by the extra block row (S_end = end of the zero tile past the last tile)
   int xmode, B;    // xmode 1: `g` is a layer INPUT for the weight gradient: scale c / s_n from the amax array (read only)
 };
 __global__ void __launch_bounds__(256) iaf_dg_image_kernel(const IafDgImageParams p) {
   // one block per sample: max |g| of the sample, then its slots of the operand image (pad slots as zeros)
   __shared__ float red[256];
   const int n = blockIdx.x, tid = threadIdx.x;
+  if (n == p.B) {
+    // one extra block row: zero the slots past the batch (up to the end of the zero tile).  The images outlive a call, a
+    // smaller batch after a larger one must not leave the old samples' slots behind: the weight gradient sums over every
+    // slot of every K tile
+    const int nchunk_all = p.planes >> 3;
+    const int c_lo = (int)((long long)nchunk_all * blockIdx.y / gridDim.y), c_hi = (int)((long long)nchunk_all * (blockIdx.y + 1) / gridDim.y);
+    const int s0 = p.B * p.SPS, tail = p.S_end - s0;
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < (c_hi - c_lo) * tail; i += 256) {
+      const int c = c_lo + i / tail, r = i % tail;
+      const size_t go = ((size_t)c * p.S_pad + s0 + r) * 8;
+      *reinterpret_cast<uint4*>(p.o_hi + go) = zero;
+      *reinterpret_cast<uint4*>(p.o_lo + go) = zero;
+    }
+    return;
+  }
   const float* g = p.g + (size_t)n * p.planes * p.HW;
   float m = 0.f;
   if (p.xmode) {
@@ -2032,7 +2049,8 @@ int iaf_dg_begin(IafDgPlan* pl, const float* g_heads, int B, cudaStream_t stream
   q.flip = d.variant == IAF_VARIANT_THEANO ? 0 : 1;  // the data gradient runs on the point-reflected stream of the forward
   q.xmode = 0; q.B = B;
   // gridDim.y splits the image planes; every y-block recomputes the sample's max (L2 hits) and writes the same value
-  iaf_dg_image_kernel<<<dim3(B, std::max(1, q.planes / 16)), 256, 0, stream>>>(q);
+  q.S_end = ((B * q.SPS + TC_TILE - 1) / TC_TILE + 1) * TC_TILE;
+  iaf_dg_image_kernel<<<dim3(B + 1, std::max(1, q.planes / 16)), 256, 0, stream>>>(q);
   return cudaGetLastError() == cudaSuccess ? IAF_OK : IAF_ERR_CUDA;
 }
 
@@ -2108,7 +2126,8 @@ int iaf_wg_run(IafDgPlan* pl, int j, const float* x, int g_buf, float* part, int
     q.planes = cin; q.H = d.H; q.W = d.W; q.Wp = d.W + 1; q.SPS = SPS; q.HW = d.H * d.W; q.S_pad = pl->img_S_pad;
     q.flip = d.variant == IAF_VARIANT_THEANO ? 0 : 1;
     q.xmode = 1; q.B = B;
-    iaf_dg_image_kernel<<<dim3(B, std::max(1, cin / 32)), 256, 0, stream>>>(q);
+    q.S_end = ((B * SPS + TC_TILE - 1) / TC_TILE + 1) * TC_TILE;
+    iaf_dg_image_kernel<<<dim3(B + 1, std::max(1, cin / 32)), 256, 0, stream>>>(q);
     if (cudaGetLastError() != cudaSuccess) return IAF_ERR_CUDA;
   }
   IafWgTcParams q;

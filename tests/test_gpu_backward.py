@@ -245,3 +245,29 @@ def test_tensor_core_backward_is_scale_invariant():
         for a, b in zip(out[0], other):
             assert torch.isfinite(b).all()
             assert float((a.double() - b.double()).abs().max()) <= 1e-5 * max(float(a.abs().max()), 1e-30)
+
+
+def test_tensor_core_backward_after_a_larger_batch():
+    """The operand images of the tensor-core backward outlive a call: a smaller batch after a larger one must give what a
+    fresh operator gives (the weight gradient sums over every slot of every K tile, so stale slots would show up there)."""
+    variant, n_z, hidden, H, W, nl = "tf", 32, [64], 16, 16, "elu"
+
+    def run(op, dev, B):
+        z, ctx = O.make_inputs(B, n_z, hidden[0], H, W, seed=3)
+        zg = torch.from_numpy(z).cuda().requires_grad_(True)
+        cg = torch.from_numpy(ctx).cuda().requires_grad_(True)
+        for l in dev:
+            for t in l:
+                t.grad = None
+        zo, ls, ld = op.step(zg, cg)
+        (zo.sum() + 0.5 * ls.sum() - ld.sum()).backward()
+        return [zg.grad.clone(), cg.grad.clone()] + [t.grad.clone() for l in dev for t in l]
+
+    op, dev = _build(variant, n_z, hidden, [n_z, n_z], H, W, 2, nl)[:2]
+    assert op.backward_path(H, W, "cuda") == "tc"
+    run(op, dev, 9)
+    got = run(op, dev, 5)
+    op2, dev2 = _build(variant, n_z, hidden, [n_z, n_z], H, W, 2, nl)[:2]
+    want = run(op2, dev2, 5)
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
