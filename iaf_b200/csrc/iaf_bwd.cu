@@ -1014,8 +1014,16 @@ int iaf_bwd_run(IafBwdPlan* pl, const IafBwdArgs* a, cudaStream_t stream, int* n
   }
 
   // ---- 2. gradient at the heads ----
+  const bool fused_step = pl->dg && pl->wg_tc && a->mode == IAF_MODE_STEP && saved && iaf_dg_step_supported(pl->dg);
+  const float* step_bias = nullptr;
   if (layer) {
     IAF_LAUNCH(iaf_bwd_layer_affine_kernel, ew_grid((size_t)B * pl->head_pad * HW), BW_THREADS, 0, stream, lq);
+  } else if (a->mode == IAF_MODE_STEP && fused_step) {
+    // tensor-core backward with kept activations: affine backward, per-sample scale, heads' bias sums and gradient image in
+    // one launch (iaf_dg_step_kernel); the fp32 heads gradient is not needed by anything downstream
+    if ((st = iaf_dg_begin_step(pl->dg, a->z_out_saved, a->logsd_saved, a->g_zout, a->g_logsd, a->g_logdet, a->g_z, nullptr,
+                                pl->head_pad, B, stream, &step_bias)) != IAF_OK)
+      return st;
   } else if (a->mode == IAF_MODE_STEP) {
     IafAffineBwdParams q;
     memset(&q, 0, sizeof(q));
@@ -1042,8 +1050,10 @@ int iaf_bwd_run(IafBwdPlan* pl, const IafBwdArgs* a, cudaStream_t stream, int* n
   int g_planes = pl->ncol[last];
   for (int j = last; j >= 0; --j) {
     const float* xin = hcur[j];
-    if (pl->dg && j == last && (st = iaf_dg_begin(pl->dg, Gcur, B, stream)) != IAF_OK) return st;
-    if (pl->dg && j == last) ++nl_;
+    if (pl->dg && j == last && !fused_step) {
+      if ((st = iaf_dg_begin(pl->dg, Gcur, B, stream)) != IAF_OK) return st;
+      ++nl_;
+    }
     if (want_params && pl->dg && pl->wg_tc) {
       // tensor cores: X^T G per tap over the slot stream as K (iaf_wg.cuh); bias / pad-channel sums separately
       const int nw = IAF_NTAPS * pl->cin[j] * pl->ncol[j];
@@ -1052,15 +1062,22 @@ int iaf_bwd_run(IafBwdPlan* pl, const IafBwdArgs* a, cudaStream_t stream, int* n
       if ((st = iaf_wg_run(pl->dg, j, xin, (last - j) & 1, pl->part, n, pl->NG[j], B, stream, &ng)) != IAF_OK) return st;
       IAF_LAUNCH(iaf_bwd_reduce_kernel, (nw + 31) / 32, BW_THREADS, 0, stream, (const float*)pl->part, pl->dwp[j], nw, ng, n);
       if (cudaGetLastError() != cudaSuccess) return IAF_ERR_CUDA;
+      if (fused_step && j == last) {  // the prologue left per-sample sums: [B][5][ncol]
+        IAF_LAUNCH(iaf_bwd_reduce_kernel, (5 * pl->ncol[j] + 31) / 32, BW_THREADS, 0, stream, step_bias, pl->dwp[j] + nw,
+                   5 * pl->ncol[j], B, 5 * pl->ncol[j]);
+        if (cudaGetLastError() != cudaSuccess) return IAF_ERR_CUDA;
+        nl_ += 4;
+      } else {
 #ifndef IAF_EMU
-      if (flip) iaf_bwd_bias_kernel<true><<<pl->ncol[j] * BW_BIAS_SEG, BW_THREADS, 0, stream>>>(Gcur, pl->bpart, B, g_planes, pl->ncol[j], H, W, flip);
-      else iaf_bwd_bias_kernel<false><<<pl->ncol[j] * BW_BIAS_SEG, BW_THREADS, 0, stream>>>(Gcur, pl->bpart, B, g_planes, pl->ncol[j], H, W, flip);
+        if (flip) iaf_bwd_bias_kernel<true><<<pl->ncol[j] * BW_BIAS_SEG, BW_THREADS, 0, stream>>>(Gcur, pl->bpart, B, g_planes, pl->ncol[j], H, W, flip);
+        else iaf_bwd_bias_kernel<false><<<pl->ncol[j] * BW_BIAS_SEG, BW_THREADS, 0, stream>>>(Gcur, pl->bpart, B, g_planes, pl->ncol[j], H, W, flip);
 #endif
-      if (cudaGetLastError() != cudaSuccess) return IAF_ERR_CUDA;
-      IAF_LAUNCH(iaf_bwd_reduce_kernel, (5 * pl->ncol[j] + 31) / 32, BW_THREADS, 0, stream, (const float*)pl->bpart,
-                 pl->dwp[j] + nw, 5 * pl->ncol[j], BW_BIAS_SEG, 5 * pl->ncol[j]);
-      if (cudaGetLastError() != cudaSuccess) return IAF_ERR_CUDA;
-      nl_ += 5;
+        if (cudaGetLastError() != cudaSuccess) return IAF_ERR_CUDA;
+        IAF_LAUNCH(iaf_bwd_reduce_kernel, (5 * pl->ncol[j] + 31) / 32, BW_THREADS, 0, stream, (const float*)pl->bpart,
+                   pl->dwp[j] + nw, 5 * pl->ncol[j], BW_BIAS_SEG, 5 * pl->ncol[j]);
+        if (cudaGetLastError() != cudaSuccess) return IAF_ERR_CUDA;
+        nl_ += 5;
+      }
     } else if (want_params) {
       IafWgradParams q;
       memset(&q, 0, sizeof(q));

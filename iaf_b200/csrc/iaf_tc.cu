@@ -1841,6 +1841,8 @@ struct IafDgPlan {
   __nv_bfloat16* ximg[2];    // weight gradient: operand image of the current layer's input [hi | lo]
   int img_S_pad, scratch_B;
   float* amax;               // [B]
+  float* bstep;              // [B][5][kin[last]]: per-sample bias / pad-channel sums of the fused step prologue
+  int step_optin;            // the prologue kernel's dynamic shared memory limit has been raised
   int num_sms;
 };
 
@@ -1939,6 +1941,7 @@ void iaf_dg_plan_destroy(IafDgPlan* pl) {
   }
   if (pl->zeros) cudaFree(pl->zeros);
   if (pl->amax) cudaFree(pl->amax);
+  if (pl->bstep) cudaFree(pl->bstep);
   for (int a = 0; a < 2; ++a)
     for (int b = 0; b < 2; ++b)
       if (pl->img[a][b]) cudaFree(pl->img[a][b]);
@@ -2030,8 +2033,10 @@ static int dg_ensure_scratch(IafDgPlan* pl, int B) {
     if (cudaMemset(pl->ximg[a], 0, bytes) != cudaSuccess) return IAF_ERR_CUDA;
   }
   if (pl->amax) cudaFree(pl->amax);
-  pl->amax = nullptr;
+  if (pl->bstep) cudaFree(pl->bstep);
+  pl->amax = pl->bstep = nullptr;
   if (cudaMalloc(&pl->amax, sizeof(float) * (size_t)B) != cudaSuccess) return IAF_ERR_CUDA;
+  if (cudaMalloc(&pl->bstep, sizeof(float) * (size_t)B * 5 * pl->kin[pl->n_stages - 1]) != cudaSuccess) return IAF_ERR_CUDA;
   pl->scratch_B = B;
   return IAF_OK;
 }
@@ -2154,5 +2159,143 @@ int iaf_wg_run(IafDgPlan* pl, int j, const float* x, int g_buf, float* part, int
   const size_t smem = (size_t)q.n_stages * q.stage_bytes + slack;
   iaf_wg_kernel<<<ntiles * q.NG, WG_THREADS, smem, stream>>>(q);
   if (ng_used) *ng_used = q.NG;
+  return cudaGetLastError() == cudaSuccess ? IAF_OK : IAF_ERR_CUDA;
+}
+
+struct IafDgStepParams {
+  const float* z_out; const float* logsd; const float* g_zout; const float* g_logsd; const float* g_logdet;
+  float* g_z; float* hb; float* bstep; float* amax;
+  __nv_bfloat16* o_hi; __nv_bfloat16* o_lo;
+  int B, C, cp, head_pad, H, W, Wp, SPS, HW, S_pad, S_end, fwd_flip, img_flip;
+  float scale;
+};
+
+// ------------------------------------------------------------------------------------------
+// Fused prologue of the tensor-core backward of the STEP entry with kept activations: what iaf_bwd_affine_kernel,
+// iaf_dg_image_kernel and the heads' iaf_bwd_bias_kernel do in three passes over [B][2 n_z][HW], in one: a block per sample
+// forms g_m, g_s (models.py:282-285 differentiated) in shared memory, writes the direct term of g_z, the sample's max and
+// scale, its bias / pad-channel column sums, and the scaled operand image of the heads' gradient.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) iaf_dg_step_kernel(const __grid_constant__ IafDgStepParams p) {
+  extern __shared__ float sg[];  // [cp][HW]
+  __shared__ float red[256];
+  const int n = blockIdx.x, tid = threadIdx.x, HW = p.HW;
+  if (n == p.B) {  // zero the image slots past the batch (see iaf_dg_image_kernel)
+    const int nchunk = p.cp >> 3;
+    const int s0 = p.B * p.SPS, tail = p.S_end - s0;
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < nchunk * tail; i += 256) {
+      const size_t go = ((size_t)(i / tail) * p.S_pad + s0 + i % tail) * 8;
+      *reinterpret_cast<uint4*>(p.o_hi + go) = zero;
+      *reinterpret_cast<uint4*>(p.o_lo + go) = zero;
+    }
+    return;
+  }
+  for (int i = tid; i < p.cp * HW; i += 256) sg[i] = 0.f;
+  __syncthreads();
+  float m = 0.f;
+  const float gld = p.g_logdet ? __ldg(p.g_logdet + n) : 0.f;
+  for (int i = tid; i < p.C * HW; i += 256) {
+    const int c = i / HW, gp = i - c * HW;
+    const int mcol = (c >> 2) * 8 + (c & 3), scol = mcol + 4;
+    const size_t e = ((size_t)n * p.C + c) * HW + gp;
+    const float ex = expf(-__ldg(p.logsd + e)), zn = __ldg(p.z_out + e), gzo = __ldg(p.g_zout + e);
+    float gs = -p.scale * zn * gzo;
+    if (p.g_logsd) gs += p.scale * __ldg(p.g_logsd + e);
+    gs -= p.scale * gld;
+    const float gm = -p.scale * ex * gzo;
+    sg[mcol * HW + gp] = gm;
+    sg[scol * HW + gp] = gs;
+    p.g_z[e] = ex * gzo;
+    if (p.hb) {
+      p.hb[((size_t)n * p.cp + mcol) * HW + gp] = gm;
+      p.hb[((size_t)n * p.cp + scol) * HW + gp] = gs;
+    }
+    m = fmaxf(m, fmaxf(fabsf(gm), fabsf(gs)));
+  }
+  red[tid] = m;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (tid < s) red[tid] = fmaxf(red[tid], red[tid + s]);
+    __syncthreads();
+  }
+  m = red[0];
+  if (tid == 0) p.amax[n] = m;
+  const float sc = dg_scale_from_amax(m);
+  // column sums of this sample (fixed order: lane-strided, xor-shuffle tree); warp w owns columns w, w + 8, ...
+  {
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int col = warp; col < p.cp; col += 8) {
+      float s5[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int gp = lane; gp < HW; gp += 32) {
+        const float v = sg[col * HW + gp];
+        const int pix = p.fwd_flip ? HW - 1 - gp : gp;  // logical position of this memory pixel
+        const int y = pix / p.W, x = pix - y * p.W;
+        const bool byH = (y == p.H - 1), bx0 = (x == 0), bxW = (x == p.W - 1);
+        s5[0] += v;
+        s5[1] += bxW ? v : 0.f;
+        s5[2] += (byH || bx0) ? v : 0.f;
+        s5[3] += byH ? v : 0.f;
+        s5[4] += (byH || bxW) ? v : 0.f;
+      }
+#pragma unroll
+      for (int t = 0; t < 5; ++t) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s5[t] += __shfl_xor_sync(0xffffffffu, s5[t], o);
+        if (lane == 0) p.bstep[((size_t)n * 5 + t) * p.cp + col] = s5[t];
+      }
+    }
+  }
+  // operand image of the sample (point-reflected stream of the forward), pad slots as zeros
+  const int nchunk = p.cp >> 3;
+  for (int i = tid; i < nchunk * p.SPS; i += 256) {
+    const int c = i / p.SPS, r = i - c * p.SPS;
+    const int y = r / p.Wp, x = r - y * p.Wp;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = 0.f;
+    if (y < p.H && x < p.W) {
+      const int pix = y * p.W + x;
+      const int gp = p.img_flip ? HW - 1 - pix : pix;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = sg[(c * 8 + e) * HW + gp] * sc;
+    }
+    const size_t go = ((size_t)c * p.S_pad + (size_t)n * p.SPS + r) * 8;
+    split_store8(v, reinterpret_cast<uint8_t*>(p.o_hi + go), reinterpret_cast<uint8_t*>(p.o_lo + go));
+  }
+}
+
+bool iaf_dg_step_supported(const IafDgPlan* pl) {
+  const char* e = getenv("IAF_BWD_FUSED_PROLOGUE");
+  if (e && e[0] == '0') return false;
+  return (size_t)pl->kin[pl->n_stages - 1] * pl->d.H * pl->d.W * 4 <= 160 * 1024;
+}
+
+// STEP entry with kept activations: g_z (direct term), per-sample scale, bias sums (-> *bias_partials, [B][5][cp]) and the
+// operand image 0 of the heads' gradient in one launch.  hb (fp32 heads gradient) is optional.
+int iaf_dg_begin_step(IafDgPlan* pl, const float* z_out, const float* logsd, const float* g_zout, const float* g_logsd,
+                      const float* g_logdet, float* g_z, float* hb, int head_pad, int B, cudaStream_t stream,
+                      const float** bias_partials) {
+  const iaf_desc_t& d = pl->d;
+  int st = dg_ensure_scratch(pl, B);
+  if (st != IAF_OK) return st;
+  if (!pl->step_optin) {
+    if (iaf_smem_optin(iaf_dg_step_kernel) != cudaSuccess) return IAF_ERR_CUDA;
+    pl->step_optin = 1;
+  }
+  IafDgStepParams q;
+  memset(&q, 0, sizeof(q));
+  q.z_out = z_out; q.logsd = logsd; q.g_zout = g_zout; q.g_logsd = g_logsd; q.g_logdet = g_logdet;
+  q.g_z = g_z; q.hb = hb; q.bstep = pl->bstep; q.amax = pl->amax;
+  q.o_hi = pl->img[0][0]; q.o_lo = pl->img[0][1];
+  q.B = B; q.C = d.n_z; q.cp = pl->kin[pl->n_stages - 1]; q.head_pad = head_pad;
+  q.H = d.H; q.W = d.W; q.Wp = d.W + 1; q.SPS = (d.H + 1) * (d.W + 1); q.HW = d.H * d.W;
+  q.S_pad = pl->img_S_pad;
+  q.S_end = ((B * q.SPS + TC_TILE - 1) / TC_TILE + 1) * TC_TILE;
+  q.fwd_flip = d.variant == IAF_VARIANT_THEANO ? 1 : 0;
+  q.img_flip = q.fwd_flip ? 0 : 1;
+  q.scale = 0.1f;
+  iaf_dg_step_kernel<<<B + 1, 256, (size_t)q.cp * q.HW * 4, stream>>>(q);
+  if (bias_partials) *bias_partials = pl->bstep;
   return cudaGetLastError() == cudaSuccess ? IAF_OK : IAF_ERR_CUDA;
 }

@@ -38,3 +38,7 @@ int iaf_dg_stage(IafDgPlan* p, int j, const float* w_packed, int in_buf, const f
                  int B, cudaStream_t stream);
 int iaf_wg_run(IafDgPlan* p, int j, const float* x, int g_buf, float* part, int part_stride, int ng_max, int B,
                cudaStream_t stream, int* ng_used);
+bool iaf_dg_step_supported(const IafDgPlan* p);
+int iaf_dg_begin_step(IafDgPlan* p, const float* z_out, const float* logsd, const float* g_zout, const float* g_logsd,
+                      const float* g_logdet, float* g_z, float* hb, int head_pad, int B, cudaStream_t stream,
+                      const float** bias_partials);

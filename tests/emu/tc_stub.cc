@@ -13,3 +13,6 @@ void iaf_dg_plan_destroy(IafDgPlan*) {}
 int iaf_dg_begin(IafDgPlan*, const float*, int, cudaStream_t) { return IAF_ERR_UNSUPPORTED; }
 int iaf_dg_stage(IafDgPlan*, int, const float*, int, const float*, float*, int, int, cudaStream_t) { return IAF_ERR_UNSUPPORTED; }
 int iaf_wg_run(IafDgPlan*, int, const float*, int, float*, int, int, int, cudaStream_t, int*) { return IAF_ERR_UNSUPPORTED; }
+bool iaf_dg_step_supported(const IafDgPlan*) { return false; }
+int iaf_dg_begin_step(IafDgPlan*, const float*, const float*, const float*, const float*, const float*, float*, float*, int, int,
+                      cudaStream_t, const float**) { return IAF_ERR_UNSUPPORTED; }

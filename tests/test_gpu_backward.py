@@ -269,5 +269,7 @@ def test_tensor_core_backward_after_a_larger_batch():
     got = run(op, dev, 5)
     op2, dev2 = _build(variant, n_z, hidden, [n_z, n_z], H, W, 2, nl)[:2]
     want = run(op2, dev2, 5)
+    # not bit-equal: the number of split-K groups of the weight gradient is fixed when the scratch is sized (for the larger
+    # batch here), so the summation order differs; slots left over from the larger batch would be an O(1) error
     for a, b in zip(got, want):
-        assert torch.equal(a, b)
+        assert float((a.double() - b.double()).abs().max()) <= 1e-5 * max(float(b.abs().max()), 1e-30)
