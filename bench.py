@@ -281,8 +281,10 @@ def cpu_arm(name, steps, warmup):
         cand_ms[c] = statistics.median(_timed_calls(fn, 3, 5)) * 1e3
     best = min(cand_ms, key=cand_ms.get)
     torch.set_num_threads(best)
-    steps = max(5, min(steps, 50))
-    warmup = max(3, min(warmup, 5))
+    # at least 20 timed calls whatever K is: single calls on a shared host scatter by an order of magnitude (10 ms median,
+    # 170 ms maximum seen on the GPU boxes), and the two arms must report the same number for the same routine
+    steps = max(20, min(steps, 50))
+    warmup = max(5, min(warmup, 10))
     ts = _timed_calls(fn, warmup, steps)
     t = statistics.median(ts)
     info = {"value": elems / t, "unit": UNIT, "cores": best, "kind": "port",

@@ -36,8 +36,8 @@ __device__ __forceinline__ void commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // fp16 A and B, fp32 accumulate, M = 128, BOTH operands MN-major (bits 15 and 16)
-__device__ __forceinline__ uint32_t idesc_mn(int N) {
-  return (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+__device__ __forceinline__ uint32_t idesc_mn(int N, int M = 128) {
+  return (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 __device__ __forceinline__ uint64_t mk_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {  // SWIZZLE_NONE
   const uint32_t lo = ((saddr >> 4) & 0x3FFFu) | (((lbo >> 4) & 0x3FFFu) << 16);
@@ -48,10 +48,10 @@ __device__ __forceinline__ uint64_t mk_desc(uint32_t saddr, uint32_t lbo, uint32
 constexpr int SLOTS = 192;  // slots per chunk plane (K extent incl. room for shifts)
 constexpr int MA = 128;     // A channels (M)
 constexpr int KT = 64;      // slots contracted (4 MMAs of K = 16)
-__host__ __device__ inline int a_val(int m, int s) { return (m * 3 + s * 5) % 7 - 3; }
+__host__ __device__ inline int a_val(int m, int s) { return (m * 3 + s * 5) % 7 - 3 + (s == (m & 63) ? 2 : 0); }  // rows pairwise different
 __host__ __device__ inline int b_val(int n, int s) { return (n + 2 * s) % 9 - 4; }
 
-struct Cfg { int N; int shift; int swap; };  // swap 0: LBO = 128 (K groups), SBO = plane pitch (MN groups); 1: the other way round
+struct Cfg { int N; int shift; int swap; int M; };  // M = 128 or 64  // swap 0: LBO = 128 (K groups), SBO = plane pitch (MN groups); 1: the other way round
 
 __global__ void __launch_bounds__(128, 1) k_mn(Cfg c, float* D) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(128, 1) k_mn(Cfg c, float* D) {
     for (int ks = 0; ks < KT / 16; ++ks) {
       const uint64_t ad = mk_desc(smem_u32(A) + (uint32_t)(ks * 16) * 16u, lbo, sbo);
       const uint64_t bd = mk_desc(smem_u32(B) + (uint32_t)(ks * 16 + c.shift) * 16u, lbo, sbo);
-      umma(d, ad, bd, idesc_mn(N), ks ? 1u : 0u);
+      umma(d, ad, bd, idesc_mn(N, c.M), ks ? 1u : 0u);
     }
     commit(&bar);
   }
@@ -117,7 +117,7 @@ int main() {
   for (int N : {64, 160})
     for (int swap = 0; swap < 2; ++swap)
       for (int shift : {0, 1, 8, 17, 18}) {
-        Cfg c{N, shift, swap};
+        Cfg c{N, shift, swap, 128};
         const size_t smem = (size_t)(MA / 8 + N / 8) * SLOTS * 16 + 1024;
         cudaMemset(dD, 0, 128 * 256 * 4);
         k_mn<<<1, 128, smem>>>(c, dD);
@@ -137,5 +137,31 @@ int main() {
                e == cudaSuccess ? "" : cudaGetErrorString(e));
         if (e != cudaSuccess) return 1;
       }
+  // ---- M = 64: where do the 64 rows of D land in the 128 TMEM lanes? ----
+  {
+    const int N = 64;
+    Cfg c{N, 1, 0, 64};
+    const size_t smem = (size_t)(MA / 8 + N / 8) * SLOTS * 16 + 1024;
+    cudaMemset(dD, 0xff, 128 * 256 * 4);  // NaN pattern: untouched lanes stay recognisable
+    k_mn<<<1, 128, smem>>>(c, dD);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    std::vector<float> hD((size_t)128 * N);
+    cudaMemcpy(hD.data(), dD, hD.size() * 4, cudaMemcpyDeviceToHost);
+    printf("M=64 N=64 shift=1: %s\n", e == cudaSuccess ? "ran" : cudaGetErrorString(e));
+    for (int m = 0; m < 64; ++m) {
+      int found = -1, nfound = 0;
+      for (int lane = 0; lane < 128; ++lane) {
+        bool all = true;
+        for (int n = 0; n < N && all; ++n) {
+          float ref = 0.f;
+          for (int s = 0; s < KT; ++s) ref += (float)a_val(m, s) * (float)b_val(n, s + 1);
+          all = ref == hD[(size_t)lane * N + n];
+        }
+        if (all) { if (found < 0) found = lane; ++nfound; }
+      }
+      if (m % 8 == 0 || found != m) printf("  row %2d -> lane %d (%d lanes match)\n", m, found, nfound);
+    }
+  }
   return 0;
 }
