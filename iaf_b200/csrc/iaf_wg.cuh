@@ -8,7 +8,8 @@
 // (8 K-rows x 16 bytes of 8 contiguous channels), LBO = 128 B between K groups, SBO = the plane pitch between channel
 // groups, and a tap is still `shift x 16` bytes on G's start address (tools/mma_mnmajor.cu, profiles/r2_mma_mnmajor.log:
 // exact for shifts 0 / 1 / 8 / 17 / 18).  So per tap and per 16 slots: D_tap[ci][co] += X^T G with M = 128 input channels
-// (a block; rows past the layer's channels read whatever follows in shared memory and are never stored), N = a part of
+// (a block; M = 64 for a block of at most 64; rows past the layer's channels read whatever follows in shared memory and
+// are never stored), N = a part of
 // the columns (5 accumulators of N <= 96 columns fill the 512 TMEM columns), the same three split-operand products as
 // everywhere (X_lo G_hi, X_hi G_lo, X_hi G_hi; A-operand collector on the pair).
 //
@@ -56,6 +57,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) iaf_wg_kernel(const __grid_cons
   const int x_pitch = WG_KT * 16, g_pitch = (WG_KT + WG_HALO) * 16;  // bytes per chunk plane in a stage
   const int n_my = (p.NTK - g + p.NG - 1) / p.NG;                      // K tiles u = g, g + NG, ...
   const int xpl = min(p.xplanes, (p.cin >> 3) - mb * 16);               // chunk planes this channel block really has
+  // a block with at most 64 channels issues M = 64 instructions (half the A fetch; the accumulator then sits in lanes
+  // 0-15 of every 32-lane quadrant: row m -> lane (m / 16) * 32 + m % 16, tools/mma_mnmajor.cu)
+  const bool m64 = xpl <= 8;
 
   if (warp == WG_W_MMA) {
     tmem_alloc(&s_tmem, 512u);
@@ -102,7 +106,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) iaf_wg_kernel(const __grid_cons
     }
   } else if (warp == WG_W_MMA) {
     // instruction descriptor: fp16 x fp16 -> f32, BOTH operands MN-major (bits 15, 16), M = 128, N = Np
-    const uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(p.Np >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(p.Np >> 3) << 17) | ((uint32_t)((m64 ? 64 : 128) >> 4) << 24);
     const uint32_t xh_hi = ((uint32_t)x_pitch >> 4) | (1u << 14);  // high words: SBO = plane pitch, descriptor version 1
     const uint32_t gh_hi = ((uint32_t)g_pitch >> 4) | (1u << 14);
     const uint32_t sh[IAF_NTAPS] = {0u, 1u, (uint32_t)(p.Wp - 1), (uint32_t)p.Wp, (uint32_t)(p.Wp + 1)};
@@ -138,7 +142,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) iaf_wg_kernel(const __grid_cons
     }
   } else {
     // epilogue warps: D_tap[ci][co] (lanes = input channels of this block) -> part[g][(tap * cin + ci) * ncol + co] / c
-    const int ci = mb * 128 + warp * 32 + lane;
+    const int ci = m64 ? (lane < 16 ? mb * 128 + warp * 16 + lane : p.cin) : mb * 128 + warp * 32 + lane;
     float* out = p.part + (size_t)g * p.part_stride;
     if (n_my > 0) {
       float am = 0.f;
