@@ -2017,6 +2017,7 @@ static int dg_ensure_scratch(IafDgPlan* pl, int B) {
   const int SPS = (pl->d.H + 1) * (pl->d.W + 1);
   if ((long long)B * SPS + TC_TILE >= (1LL << 31)) return IAF_ERR_UNSUPPORTED;
   const int NT = (B * SPS + TC_TILE - 1) / TC_TILE;
+  pl->scratch_B = 0;  // a failure below must not leave the old size standing over freed buffers
   pl->img_S_pad = (NT + 1) * TC_TILE;  // one zero tile past the end: windows of the last tile read into it
   const size_t bytes = (size_t)(pl->max_ch / 8) * pl->img_S_pad * 16;
   for (int a = 0; a < 2; ++a)
