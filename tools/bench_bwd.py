@@ -1,6 +1,8 @@
-"""Time the backward of the IAF step (iaf_step_bwd) on one GPU: CUDA events around K calls, inputs
-resident in HBM.  Prints one JSON line per workload.  Algorithmic flops of the backward = 3x the forward's live MACs
-(forward recompute + data gradient + weight gradient), fp32 FMA roofline (no tensor cores in this first version).
+"""Time the backward of the IAF step on one GPU: CUDA events around K calls, inputs resident in HBM.  Prints
+one JSON line per workload: `bwd_inputs_only` / `bwd_full` = iaf_step_bwd (recomputes the activations), `fwd_plain` /
+`fwd_train` = the forward without / with kept activations, `bwd_saved_full` = iaf_step_bwd_saved (what the autograd node runs).
+Algorithmic flops of the backward = 3x the forward's live MACs (recompute + data gradient + weight gradient); `algorithmic_tflops`
+is that over `bwd_full`.  Tensor-core plans run the backward on the tensor cores (IAF_BWD_TC=0: exact-fp32 SIMT kernels).
 usage: python tools/bench_bwd.py [c2a|c2b] [steps]"""
 import json
 import os
@@ -67,7 +69,8 @@ def main():
     fwd_flops = op.algorithmic_flops(B, H, W, "cuda:0")
     full = out["bwd_full"]["ms"] * 1e-3
     print(json.dumps({"workload": wl, "B": B, "steps": steps, **out,
-                      "algorithmic_flops_bwd": 3 * fwd_flops, "fp32_tflops": 3 * fwd_flops / full / 1e12,
+                      "algorithmic_flops_bwd": 3 * fwd_flops, "algorithmic_tflops": 3 * fwd_flops / full / 1e12,
+                      "backward_path": op.backward_path(H, W, "cuda:0"),
                       "latent_elems_per_s": B * n_z * H * W / full}))
 
 
