@@ -10,7 +10,7 @@ n_z=32, 16x16.  Metric: latent elements/s = 256*n_z*H*W / t_step, wh
 * value      : inputs resident in HBM.  The K steps are grouped into ELBO evaluations of E steps
                (E = the number of IAF steps per ELBO of the model the workload comes from); each group
                is one CUDA-graph replay (the E step launches, then the ELBO scalar = the sum of the
-               group's log-dets, captured in the same graph) and, at N > 1, ONE all-reduce of that scalar (tf_train.py:142), issued on a side stream so it
+               group's log-dets, captured in the same graph; at N = 1 all groups form one graph) and, at N > 1, ONE all-reduce of that scalar (tf_train.py:142), issued on a side stream so it
                overlaps the next group's kernels.  CUDA events around the whole region, max over ranks.
                The steps rotate through NSETS input/output sets whose footprint exceeds L2.
 * roofline   : the step kernel(s) alone: one CUDA graph of K back-to-back launches, CUDA events;
@@ -443,10 +443,24 @@ class DeviceBench(object):
             torch.sum(rows[r0:r0 + n].reshape(-1), dim=0, out=scal[gi])
         reduce_group(0, 0, groups[0][1])  # outside any capture first (lazy initialisation of the reduction)
         # one graph per ELBO evaluation: its E step launches and the reduction of their log-dets into scal[gi]
-        graphs = [self._capture(range(s, s + n), tail=(lambda gi=gi, s=s, n=n: reduce_group(gi, s, n)))
-                  for gi, (s, n) in enumerate(groups)]
+        # one rank: nothing happens between two evaluations (no collective), so the K steps and their reductions are ONE graph
+        whole = None
+        if self.dist is None and self.use_graph:
+            def all_groups():
+                for gi, (s, n) in enumerate(groups):
+                    for i in range(s, s + n):
+                        self.launch(i, torch.cuda.current_stream(self.device))
+                    reduce_group(gi, s, n)
+            whole = self._capture([], tail=all_groups)
+        graphs = [None] * len(groups)
+        if whole is None:
+            graphs = [self._capture(range(s, s + n), tail=(lambda gi=gi, s=s, n=n: reduce_group(gi, s, n)))
+                      for gi, (s, n) in enumerate(groups)]
 
         def run():
+            if whole is not None:
+                whole.replay()
+                return
             works = []
             for gi, (s, n) in enumerate(groups):
                 g = graphs[gi]
